@@ -1,0 +1,16 @@
+/* Compile-time switch set for the "giant_hydro" scenario, in the reference's own
+ * parameter.h vocabulary (reference: examples/giant_collisions/hydro/parameter.h).  Only switches that are
+ * non-zero or sized are listed; miluphcuda_b200/csrc/switches.h defaults every
+ * other reference switch to 0 and rejects combinations outside the hot-path scope. */
+#ifndef _PARAMETER_H
+#define _PARAMETER_H
+#define DIM 3
+#define HYDRO 1
+#define INTEGRATE_ENERGY 1
+#define INTEGRATE_DENSITY 1
+#define SPH_EQU_VERSION 1
+#define ARTIFICIAL_VISCOSITY 1
+#define MAX_NUM_INTERACTIONS 800
+#define MAX_NUM_FLAWS 1
+#define BOUNDARY_PARTICLE_ID -1
+#endif
