@@ -1,0 +1,202 @@
+/*
+ * b200sph.h -- C-ABI of the B200-native SPH right-hand side.
+ *
+ * This is the drop-in boundary for miluphcuda's per-step hot path: everything
+ * the reference's `void rightHandSide(void)` (reference: include/rhs.h:30,
+ * src/rhs.cu:143-861) launches is replaced by `b200sph_rhs_eval()`.  The
+ * reference passes its arguments through globals: the `__constant__ struct
+ * Particle p` bound by the integrator right before each call (e.g.
+ * src/rk2adaptive.cu:219,289,308), `p_rhs` (always `p_device`,
+ * src/timeintegration.cu:200-201) and the `mat*` material arrays
+ * (include/config_parameter.h:40-290).  Here they are explicit: plain structs
+ * of pointers and scalars, no C++/torch types.
+ *
+ * One shared library is built per compile-time switch set, exactly like the
+ * reference binary is built against one parameter.h (`libb200sph_<config>.so`);
+ * `b200sph_switch_hash()` lets the caller check both sides agree.
+ *
+ * All entry points return 0 on success, a negative value for CUDA/runtime
+ * errors and a positive value for model errors (reference error convention:
+ * include/cuda_utils.h:29-48 exits; src/tree.cu:917 asserts):
+ *   1  B200SPH_ERR_TOO_MANY_INTERACTIONS  (out-param: first offending particle)
+ *   2  B200SPH_ERR_BAD_ARGUMENT
+ *   3  B200SPH_ERR_SWITCH_MISMATCH
+ *   4  B200SPH_ERR_UNSUPPORTED            (switch / EOS outside the hot-path scope)
+ * `b200sph_last_error()` returns a human-readable description.
+ */
+#ifndef B200SPH_H
+#define B200SPH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SPH_ABI_VERSION 1
+
+#define B200SPH_OK 0
+#define B200SPH_ERR_TOO_MANY_INTERACTIONS 1
+#define B200SPH_ERR_BAD_ARGUMENT 2
+#define B200SPH_ERR_SWITCH_MISMATCH 3
+#define B200SPH_ERR_UNSUPPORTED 4
+#define B200SPH_ERR_CUDA (-1)
+
+/* Field-for-field mirror of the in-scope members of the reference's
+ * `struct Particle` (reference: include/miluph.h:67-275), with a layout that
+ * does not depend on the switch set: members a switch set does not have are
+ * NULL.  Scalars are arrays of n doubles/ints in the CALLER's particle order;
+ * tensors are n*DIM*DIM doubles, row-major per particle
+ * (src/timeintegration.cu:109-112); flaws are n*maxNumFlaws doubles.
+ * x,y,z,m may be the reference's tree-sized arrays; only [0,n) is touched. */
+typedef struct b200sph_particle_arrays {
+    double *x, *y, *z;
+    double *vx, *vy, *vz;
+    double *dxdt, *dydt, *dzdt;
+    double *ax, *ay, *az;
+    double *g_ax, *g_ay, *g_az;
+    double *g_local_cellsize, *g_x, *g_y, *g_z;
+    double *m, *h, *h0, *dhdt;
+    double *rho, *drhodt, *p, *e, *dedt;
+    double *S, *dSdt, *local_strain, *ep, *edotp, *plastic_f, *sigma;
+    double *R;
+    double *d, *damage_total, *dddt;
+    int *numFlaws, *numActiveFlaws;
+    double *flaws;
+    double *damage_porjutzi, *ddamage_porjutzidt;
+    double *muijmax;
+    double *pold, *alpha_jutzi, *alpha_jutzi_old, *dalphadt, *dalphadp, *dalphadrho, *f, *delpdelrho, *delpdele;
+    double *tensorialCorrectionMatrix;
+    double *cs;
+    int *noi, *materialId, *depth;
+} b200sph_particle_arrays;
+
+/* What one rightHandSide() call sees (reference globals: src/miluph.cu:50-63,
+ * include/miluph.h:366-421, src/timeintegration.cu:52-53,80-81). */
+typedef struct b200sph_view {
+    int n;                      /* numberOfParticles */
+    int n_real;                 /* numberOfRealParticles (== n without ghost particles) */
+    int max_num_flaws;          /* maxNumFlaws_host */
+    int selfgravity;            /* param.selfgravity  (-s) */
+    int decouplegravity;        /* param.decouplegravity (-g) */
+    int is_relaxation_run;      /* isRelaxationRun */
+    double theta;               /* treeTheta (-a) */
+    double grav_const;          /* gravConst (material.cfg global.c_gravity) */
+    b200sph_particle_arrays p;      /* the bound state+derivative buffer (`p`) */
+    b200sph_particle_arrays p_rhs;  /* `p_rhs` == p_device: materialId, h0, flaws, sigma,
+                                       tensorialCorrectionMatrix, plastic_f, R, g_x/y/z, g_local_cellsize */
+} b200sph_view;
+
+/* Per-material tables, one entry per material ID, named after the reference's
+ * device symbols (include/config_parameter.h:180-290; filled from material.cfg
+ * in src/config_parameter.cu:357-878).  Pointers may be host or device memory
+ * (copied with cudaMemcpyDefault); unused tables may be NULL (read as 0). */
+typedef struct b200sph_materials {
+    int n_materials;
+    const int *matEOS;
+    const double *matSml;
+    const double *mat_f_sml_min, *mat_f_sml_max;
+    const double *matAlpha, *matBeta;
+    const double *matPolytropicK, *matPolytropicGamma, *matIsothermalSoundSpeed;
+    const double *matBulkmodulus, *matShearmodulus, *matYoungModulus, *matYieldStress;
+    const double *matRho0, *matN, *matRhoLimit, *matcsLimit;
+    const double *matTillRho0, *matTillA, *matTillB, *matTillE0, *matTillEiv, *matTillEcv;
+    const double *matTilla, *matTillb, *matTillAlpha, *matTillBeta;
+    const double *matCohesion, *matCohesionDamaged, *matInternalFriction, *matInternalFrictionDamaged;
+    const double *matMeltEnergy;
+    const double *matDensityFloor, *matEnergyFloor;
+    const int *matdensity_via_kernel_sum;
+    const double *matexponent_tensor, *matepsilon_stress, *matmean_particle_distance;
+    const double *matporjutzi_p_elastic, *matporjutzi_p_transition, *matporjutzi_p_compacted;
+    const double *matporjutzi_alpha_0, *matporjutzi_alpha_e, *matporjutzi_alpha_t;
+    const double *matporjutzi_n1, *matporjutzi_n2;
+    const double *matcs_porous, *matcs_solid;
+    const int *matcrushcurve_style;
+    /* tabulated EOS in ANEOS format (reference: src/aneos.cu:119-181; include/config_parameter.h:140-163):
+     * per material start offsets into the concatenated axes / linearised [i_rho*n_e + i_e] tables, -1 if not ANEOS */
+    const int *aneos_n_rho, *aneos_n_e, *aneos_rho_id, *aneos_e_id, *aneos_matrix_id;
+    const double *aneos_rho, *aneos_e, *aneos_p, *aneos_cs;
+    const double *aneos_bulk_cs, *aneos_gamma;
+    int64_t aneos_rho_len, aneos_e_len, aneos_matrix_len;
+} b200sph_materials;
+
+/* Launch/timing counters of the most recent b200sph_rhs_eval*(). */
+typedef struct b200sph_stats {
+    int kernel_launches;        /* kernels of this library launched by the call */
+    int n_cells;                /* cells of the search grid */
+    int max_noi;                /* max number of interactions found */
+    int64_t total_noi;          /* sum of noi */
+    double cell_size;
+    float ms_total;             /* device time of the call (cudaEvent pair on the library stream) */
+    float ms_sort, ms_neighbours, ms_density, ms_pointwise, ms_correction, ms_forces, ms_gravity, ms_scatter;
+    int gravity_recomputed;     /* 1 if the Barnes-Hut walk ran, 0 if the stored g_a was re-added */
+} b200sph_stats;
+
+typedef struct b200sph_handle b200sph_handle;
+
+int b200sph_abi_version(void);
+/* name of the switch set this library was built for ("sedov", "impact", ...) */
+const char *b200sph_config_name(void);
+/* FNV-1a hash over "NAME=value;" of every switch in miluphcuda_b200/csrc/switches.h */
+uint64_t b200sph_switch_hash(void);
+/* value of one compile-time switch by its parameter.h name, -999 if unknown */
+int b200sph_switch_value(const char *name);
+
+/* Owns every scratch buffer (sorted SoA copies, cell grid, neighbour lists, tree); no allocation
+ * happens inside rhs_eval (reference: scratch is cudaMalloc'ed per call, src/rhs.cu:293,760). */
+int b200sph_create(b200sph_handle **out, int n_max, int device, uint64_t expected_switch_hash);
+int b200sph_destroy(b200sph_handle *h);
+const char *b200sph_last_error(const b200sph_handle *h);
+
+/* Host-side reader of material.cfg (libconfig format) -> tables with the reference's keys,
+ * defaults and derived values (replaces the parsing half of transferMaterialsToGPU(),
+ * src/config_parameter.cu:346-878; ANEOS tables as src/aneos.cu:119-181).  The returned
+ * object owns its arrays (host memory); release with b200sph_materials_free(). */
+int b200sph_materials_load(const char *cfg_path, b200sph_materials **out, double *grav_const,
+                           char *err, size_t errlen);
+void b200sph_materials_free(b200sph_materials *m);
+
+/* replaces transferMaterialsToGPU()'s uploads (src/config_parameter.cu:880-1400) */
+int b200sph_set_materials(b200sph_handle *h, const b200sph_materials *mat);
+
+/* The hot path.  Pointers in `view` are DEVICE pointers.  The call is complete on return
+ * (the reference synchronises after every kernel, e.g. src/rhs.cu:182-840).
+ * `offender` (may be NULL) receives the caller index of the first particle that exceeded
+ * MAX_NUM_INTERACTIONS when the return value is B200SPH_ERR_TOO_MANY_INTERACTIONS. */
+int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int *offender);
+
+/* Same call with HOST pointers in `view`: state fields are copied host->device, the RHS runs,
+ * and every field the integrators/writer read back is copied device->host
+ * (reference: copy_particle_data_to_device, src/memory_handling.cu:1108;
+ * copyToHostAndWriteToFile, src/io.cu:3066-3162).  Byte counts are returned in h2d/d2h. */
+int b200sph_rhs_eval_host(b200sph_handle *h, const b200sph_view *host_view, int *offender,
+                          int64_t *h2d_bytes, int64_t *d2h_bytes);
+
+/* Cold calls the reference makes outside rightHandSide():
+ * calculatePressure by the writer and the PC integrators (src/io.cu:3039, src/predictor_corrector.cu:829),
+ * damageLimit at output (src/rk2adaptive.cu:468), initializeSoundspeed at start (src/timeintegration.cu:206). */
+int b200sph_pressure(b200sph_handle *h, const b200sph_view *view);
+int b200sph_damage_limit(b200sph_handle *h, const b200sph_view *view);
+int b200sph_init_soundspeed(b200sph_handle *h, const b200sph_view *view);
+
+/* Neighbour lists of the last rhs_eval in the caller's indexing, for parity checks and for the
+ * reference writer's /number_of_interactions: row i holds noi[i] neighbour ids (unordered).
+ * `interactions` is a device buffer of n*max_per_row ints (the reference's dense layout,
+ * src/tree.cu:866), unused slots are set to -1 (src/rhs.cu:115-118). */
+int b200sph_export_interactions(b200sph_handle *h, int *interactions, int max_per_row);
+
+int b200sph_get_stats(const b200sph_handle *h, b200sph_stats *out);
+
+/* Multi-GPU.  Each rank owns a contiguous slab of the global search grid; halo
+ * particles received from neighbouring ranks are appended after the owned ones ([n_owned, n)).
+ * rhs_eval computes all rates for owned particles only; pointwise quantities are recomputed on
+ * halo copies.  n_owned == 0 or == n means single-GPU. */
+int b200sph_set_owned(b200sph_handle *h, int n_owned);
+/* Global bounding box (allreduced by the host) so every rank builds the same cells/tree. */
+int b200sph_set_global_domain(b200sph_handle *h, const double lo[3], const double hi[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPH_H */

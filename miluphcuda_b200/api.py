@@ -1,0 +1,329 @@
+"""ctypes binding of include/b200sph.h and the host-side mirror of the reference's
+`rightHandSide()` interface.
+
+The product is the C-ABI library `libb200sph_<config>.so` (hand-written sm_100a CUDA,
+built by `miluphcuda_b200.build`).  This module is what tests and bench.py use to call
+it; PyTorch only provides device memory.  There is no CPU fallback: if the library
+for a config is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+# ----------------------------------------------------------------------------- ABI mirror
+PARTICLE_FIELDS = (
+    "x", "y", "z", "vx", "vy", "vz", "dxdt", "dydt", "dzdt", "ax", "ay", "az", "g_ax", "g_ay", "g_az",
+    "g_local_cellsize", "g_x", "g_y", "g_z", "m", "h", "h0", "dhdt", "rho", "drhodt", "p", "e", "dedt",
+    "S", "dSdt", "local_strain", "ep", "edotp", "plastic_f", "sigma", "R", "d", "damage_total", "dddt",
+    "numFlaws", "numActiveFlaws", "flaws", "damage_porjutzi", "ddamage_porjutzidt", "muijmax",
+    "pold", "alpha_jutzi", "alpha_jutzi_old", "dalphadt", "dalphadp", "dalphadrho", "f", "delpdelrho", "delpdele",
+    "tensorialCorrectionMatrix", "cs", "noi", "materialId", "depth",
+)
+INT_FIELDS = frozenset({"numFlaws", "numActiveFlaws", "noi", "materialId", "depth"})
+TENSOR_FIELDS = frozenset({"S", "dSdt", "sigma", "R", "tensorialCorrectionMatrix"})
+
+MATERIAL_INT_TABLES = frozenset({
+    "matEOS", "matdensity_via_kernel_sum", "matcrushcurve_style", "aneos_n_rho", "aneos_n_e", "aneos_rho_id",
+    "aneos_e_id", "aneos_matrix_id",
+})
+MATERIAL_TABLES = (
+    "matEOS", "matSml", "mat_f_sml_min", "mat_f_sml_max", "matAlpha", "matBeta", "matPolytropicK", "matPolytropicGamma",
+    "matIsothermalSoundSpeed", "matBulkmodulus", "matShearmodulus", "matYoungModulus", "matYieldStress", "matRho0", "matN",
+    "matRhoLimit", "matcsLimit", "matTillRho0", "matTillA", "matTillB", "matTillE0", "matTillEiv", "matTillEcv", "matTilla",
+    "matTillb", "matTillAlpha", "matTillBeta", "matCohesion", "matCohesionDamaged", "matInternalFriction",
+    "matInternalFrictionDamaged", "matMeltEnergy", "matDensityFloor", "matEnergyFloor", "matdensity_via_kernel_sum",
+    "matexponent_tensor", "matepsilon_stress", "matmean_particle_distance", "matporjutzi_p_elastic",
+    "matporjutzi_p_transition", "matporjutzi_p_compacted", "matporjutzi_alpha_0", "matporjutzi_alpha_e",
+    "matporjutzi_alpha_t", "matporjutzi_n1", "matporjutzi_n2", "matcs_porous", "matcs_solid", "matcrushcurve_style",
+    "aneos_n_rho", "aneos_n_e", "aneos_rho_id", "aneos_e_id", "aneos_matrix_id", "aneos_rho", "aneos_e", "aneos_p",
+    "aneos_cs", "aneos_bulk_cs", "aneos_gamma",
+)
+
+
+class ParticleArrays(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in PARTICLE_FIELDS]
+
+
+class View(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("n_real", C.c_int), ("max_num_flaws", C.c_int), ("selfgravity", C.c_int),
+        ("decouplegravity", C.c_int), ("is_relaxation_run", C.c_int), ("theta", C.c_double), ("grav_const", C.c_double),
+        ("p", ParticleArrays), ("p_rhs", ParticleArrays),
+    ]
+
+
+class Materials(C.Structure):
+    _fields_ = (
+        [("n_materials", C.c_int)]
+        + [(name, C.c_void_p) for name in MATERIAL_TABLES]
+        + [("aneos_rho_len", C.c_int64), ("aneos_e_len", C.c_int64), ("aneos_matrix_len", C.c_int64)]
+    )
+
+    def table(self, name: str) -> np.ndarray:
+        """Host copy of one per-material table (only valid for host-resident tables)."""
+        ptr = getattr(self, name)
+        if not ptr:
+            return np.zeros(self.n_materials, dtype=np.int32 if name in MATERIAL_INT_TABLES else np.float64)
+        if name in ("aneos_rho", "aneos_e", "aneos_p", "aneos_cs"):
+            length = {"aneos_rho": self.aneos_rho_len, "aneos_e": self.aneos_e_len}.get(name, self.aneos_matrix_len)
+        else:
+            length = self.n_materials
+        ctype = C.c_int if name in MATERIAL_INT_TABLES else C.c_double
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(int(length),)).copy()
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("kernel_launches", C.c_int), ("n_cells", C.c_int), ("max_noi", C.c_int), ("total_noi", C.c_int64),
+        ("cell_size", C.c_double), ("ms_total", C.c_float), ("ms_sort", C.c_float), ("ms_neighbours", C.c_float),
+        ("ms_density", C.c_float), ("ms_pointwise", C.c_float), ("ms_correction", C.c_float), ("ms_forces", C.c_float),
+        ("ms_gravity", C.c_float), ("ms_scatter", C.c_float), ("gravity_recomputed", C.c_int),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+ERRORS = {1: "TOO_MANY_INTERACTIONS", 2: "BAD_ARGUMENT", 3: "SWITCH_MISMATCH", 4: "UNSUPPORTED", -1: "CUDA"}
+
+
+class B200SphError(RuntimeError):
+    def __init__(self, code: int, message: str, offender: int = -1):
+        super().__init__(f"b200sph error {code} ({ERRORS.get(code, '?')}): {message}")
+        self.code = code
+        self.offender = offender
+
+
+# ----------------------------------------------------------------------------- library loading
+_EXPORTS = {
+    "b200sph_abi_version": (C.c_int, []),
+    "b200sph_config_name": (C.c_char_p, []),
+    "b200sph_switch_hash": (C.c_uint64, []),
+    "b200sph_switch_value": (C.c_int, [C.c_char_p]),
+    "b200sph_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint64]),
+    "b200sph_destroy": (C.c_int, [C.c_void_p]),
+    "b200sph_last_error": (C.c_char_p, [C.c_void_p]),
+    "b200sph_materials_load": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(Materials)), C.POINTER(C.c_double), C.c_char_p, C.c_size_t]),
+    "b200sph_materials_free": (None, [C.POINTER(Materials)]),
+    "b200sph_set_materials": (C.c_int, [C.c_void_p, C.POINTER(Materials)]),
+    "b200sph_rhs_eval": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(C.c_int)]),
+    "b200sph_rhs_eval_host": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "b200sph_pressure": (C.c_int, [C.c_void_p, C.POINTER(View)]),
+    "b200sph_damage_limit": (C.c_int, [C.c_void_p, C.POINTER(View)]),
+    "b200sph_init_soundspeed": (C.c_int, [C.c_void_p, C.POINTER(View)]),
+    "b200sph_export_interactions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "b200sph_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "b200sph_set_owned": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200sph_set_global_domain": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+_LIBS: dict = {}
+
+
+def load_library(config: str) -> C.CDLL:
+    """dlopen libb200sph_<config>.so; raises if it has not been built (no fallback)."""
+    if config in _LIBS:
+        return _LIBS[config]
+    path = _build.lib_path(config)
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} is missing: build the CUDA extension first (python -m miluphcuda_b200.build {config}); "
+            "there is no CPU fallback for the SPH right-hand side")
+    lib = C.CDLL(path)
+    for name, (restype, argtypes) in _EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _LIBS[config] = lib
+    return lib
+
+
+def exported_symbols() -> tuple:
+    return tuple(_EXPORTS)
+
+
+# ----------------------------------------------------------------------------- materials
+class MaterialTables:
+    """material.cfg parsed by the library's own libconfig-format reader (host memory)."""
+
+    def __init__(self, config: str, cfg_path: str):
+        self.lib = load_library(config)
+        self._ptr = C.POINTER(Materials)()
+        g = C.c_double(0.0)
+        err = C.create_string_buffer(1024)
+        rc = self.lib.b200sph_materials_load(cfg_path.encode(), C.byref(self._ptr), C.byref(g), err, len(err))
+        if rc != 0:
+            raise B200SphError(rc, err.value.decode(errors="replace"))
+        self.grav_const = g.value
+
+    @property
+    def struct(self) -> Materials:
+        return self._ptr.contents
+
+    def pointer(self):
+        return self._ptr
+
+    def table(self, name: str) -> np.ndarray:
+        return self.struct.table(name)
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                self.lib.b200sph_materials_free(self._ptr)
+                self._ptr = C.POINTER(Materials)()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------- particle state
+def fields_for(switches: dict, selfgravity: bool = False) -> tuple:
+    """(p fields, p_rhs fields) present for a switch set -- the members of `struct Particle`
+    (reference include/miluph.h:67-275) that the hot path touches."""
+    g = lambda k: switches.get(k, 0)
+    dim = g("DIM")
+    ax = ["x", "y", "z"][:dim]
+    p = list(ax) + ["v" + a for a in ax] + ["d" + a + "dt" for a in ax] + ["a" + a for a in ax]
+    p += ["m", "h", "rho", "drhodt", "p", "e", "cs", "noi", "depth"]
+    rhs = ["materialId", "h0"]
+    if selfgravity:
+        p += ["g_a" + a for a in ax]
+        rhs += ["g_" + a for a in ax] + ["g_local_cellsize"]
+    if g("INTEGRATE_ENERGY"):
+        p.append("dedt")
+    if g("INTEGRATE_SML"):
+        p.append("dhdt")
+    if g("ARTIFICIAL_VISCOSITY"):
+        p.append("muijmax")
+    if g("SOLID"):
+        p += ["S", "dSdt", "local_strain", "ep", "edotp"]
+        rhs += ["plastic_f", "sigma"]
+    if g("TENSORIAL_CORRECTION"):
+        rhs.append("tensorialCorrectionMatrix")
+    if g("ARTIFICIAL_STRESS"):
+        rhs.append("R")
+    if g("FRAGMENTATION"):
+        p += ["d", "damage_total", "dddt", "numFlaws", "numActiveFlaws"]
+        rhs.append("flaws")
+        if g("PALPHA_POROSITY"):
+            p += ["damage_porjutzi", "ddamage_porjutzidt"]
+    if g("PALPHA_POROSITY"):
+        p += ["pold", "alpha_jutzi", "alpha_jutzi_old", "dalphadt", "dalphadp", "dalphadrho", "f", "delpdelrho", "delpdele"]
+    return tuple(p), tuple(rhs)
+
+
+def field_shape(name: str, n: int, dim: int, max_flaws: int) -> tuple:
+    if name in TENSOR_FIELDS:
+        return (n * dim * dim,)
+    if name == "flaws":
+        return (n * max(max_flaws, 1),)
+    return (n,)
+
+
+def _ptr_of(arr) -> int:
+    if arr is None:
+        return 0
+    if isinstance(arr, np.ndarray):
+        if not arr.flags["C_CONTIGUOUS"]:
+            raise ValueError("arrays passed through the C-ABI must be contiguous")
+        return arr.ctypes.data
+    return int(arr.data_ptr())  # torch tensor
+
+
+def make_view(arrays: dict, rhs_arrays: dict | None, n: int, *, n_real: int | None = None, max_num_flaws: int = 1,
+              selfgravity: bool = False, decouplegravity: bool = False, theta: float = 0.5,
+              grav_const: float = 6.67408e-11, is_relaxation_run: bool = False) -> View:
+    """Build a b200sph_view from {field: numpy array | torch tensor}.  The caller keeps the arrays alive."""
+    v = View()
+    v.n = n
+    v.n_real = n if n_real is None else n_real
+    v.max_num_flaws = max_num_flaws
+    v.selfgravity = int(selfgravity)
+    v.decouplegravity = int(decouplegravity)
+    v.is_relaxation_run = int(is_relaxation_run)
+    v.theta = theta
+    v.grav_const = grav_const
+    rhs_arrays = arrays if rhs_arrays is None else rhs_arrays
+    for name in PARTICLE_FIELDS:
+        setattr(v.p, name, _ptr_of(arrays.get(name)) or None)
+        setattr(v.p_rhs, name, _ptr_of(rhs_arrays.get(name)) or None)
+    return v
+
+
+# ----------------------------------------------------------------------------- engine
+class RhsEngine:
+    """One b200sph handle: owns the device scratch; `rhs_eval` is the drop-in for rightHandSide()."""
+
+    def __init__(self, config: str, n_max: int, device: int = 0, material_cfg: str | None = None):
+        self.config = config
+        self.lib = load_library(config)
+        self.handle = C.c_void_p()
+        rc = self.lib.b200sph_create(C.byref(self.handle), n_max, device, self.lib.b200sph_switch_hash())
+        if rc != 0:
+            raise B200SphError(rc, self.lib.b200sph_last_error(None).decode(errors="replace"))
+        self.materials = None
+        if material_cfg is not None:
+            self.set_material_cfg(material_cfg)
+
+    def _check(self, rc: int, offender: int = -1) -> None:
+        if rc != 0:
+            raise B200SphError(rc, self.lib.b200sph_last_error(self.handle).decode(errors="replace"), offender)
+
+    def set_material_cfg(self, cfg_path: str) -> MaterialTables:
+        self.materials = MaterialTables(self.config, cfg_path)
+        self._check(self.lib.b200sph_set_materials(self.handle, self.materials.pointer()))
+        return self.materials
+
+    def rhs_eval(self, view: View) -> None:
+        off = C.c_int(-1)
+        rc = self.lib.b200sph_rhs_eval(self.handle, C.byref(view), C.byref(off))
+        self._check(rc, off.value)
+
+    def rhs_eval_host(self, view: View) -> tuple:
+        off = C.c_int(-1)
+        h2d, d2h = C.c_int64(0), C.c_int64(0)
+        rc = self.lib.b200sph_rhs_eval_host(self.handle, C.byref(view), C.byref(off), C.byref(h2d), C.byref(d2h))
+        self._check(rc, off.value)
+        return h2d.value, d2h.value
+
+    def pressure(self, view: View) -> None:
+        self._check(self.lib.b200sph_pressure(self.handle, C.byref(view)))
+
+    def damage_limit(self, view: View) -> None:
+        self._check(self.lib.b200sph_damage_limit(self.handle, C.byref(view)))
+
+    def init_soundspeed(self, view: View) -> None:
+        self._check(self.lib.b200sph_init_soundspeed(self.handle, C.byref(view)))
+
+    def export_interactions(self, device_int_buffer, max_per_row: int) -> None:
+        self._check(self.lib.b200sph_export_interactions(self.handle, _ptr_of(device_int_buffer), max_per_row))
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._check(self.lib.b200sph_get_stats(self.handle, C.byref(st)))
+        return st.as_dict()
+
+    def set_owned(self, n_owned: int) -> None:
+        self._check(self.lib.b200sph_set_owned(self.handle, n_owned))
+
+    def set_global_domain(self, lo, hi) -> None:
+        if lo is None:
+            self._check(self.lib.b200sph_set_global_domain(self.handle, None, None))
+            return
+        a = (C.c_double * 3)(*[float(x) for x in lo])
+        b = (C.c_double * 3)(*[float(x) for x in hi])
+        self._check(self.lib.b200sph_set_global_domain(self.handle, a, b))
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.b200sph_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

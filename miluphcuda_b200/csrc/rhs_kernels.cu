@@ -1,0 +1,1427 @@
+/*
+ * rhs_kernels.cu -- the SPH right-hand side on one B200.
+ *
+ * Replaces the ~20 kernels miluphcuda's rightHandSide() launches
+ * (reference: src/rhs.cu:181-840) by eight:
+ *
+ *   k_prepare      floors / h clamp (boundary hooks, check_sml_boundary) + bbox + h statistics
+ *   k_cell_keys    uniform-grid cell index per particle          } replaces the lock-based octree
+ *   (cub radix sort of (cell, index))                            } build and the per-thread DFS
+ *   k_cell_start   first sorted slot of every cell               } (src/tree.cu:71-267, 786-926)
+ *   k_gather       caller order -> 32-byte cell-sorted records
+ *   k_neighbours   exact neighbour lists, tile-interleaved
+ *   k_density      kernel-sum density                            (src/density.cu:41-209)
+ *   k_pointwise    c_s, p, p-alpha, symmetrise S, damage limit, yield, sigma, artificial stress
+ *                  (src/soundspeed.cu, pressure.cu, timeintegration.cu:116, damage.cu, plasticity.cu,
+ *                   stress.cu, artificial_stress.cu -- seven reference launches fused)
+ *   k_correction   tensorial correction matrix                   (src/kernel.cu:585-713)
+ *   k_forces       pair loop + per-particle epilogue             (src/internal_forces.cu:41-1258,
+ *                  boundary.cu:215-329, velocity.cu:31-57)
+ *
+ * Particles are never reordered in the caller's buffers: every kernel after the
+ * sort works on cell-sorted scratch and writes results back through `perm`.
+ */
+#include "rhs_internal.h"
+
+#include <cub/cub.cuh>
+#include <math.h>
+#include <stdio.h>
+
+#define FULL_MASK 0xffffffffu
+
+/* ------------------------------------------------------------------ helpers */
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double coord_of(const b200sph_particle_arrays &p, int i, int axis)
+{
+#if DIM > 2
+    if (axis == 2) return p.z[i];
+#endif
+#if DIM > 1
+    if (axis == 1) return p.y[i];
+#endif
+    return p.x[i];
+}
+
+/* ------------------------------------------------------------------ k_prepare
+ * values per block: min[3], max[3], sum h, max h */
+#define PREP_VALUES 8
+#define PREP_THREADS 256
+
+__global__ void __launch_bounds__(PREP_THREADS)
+k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, int max_cells,
+          int use_global, double3 glo, double3 ghi)
+{
+    const b200sph_particle_arrays &p = v.p;
+    const b200sph_particle_arrays &pr = v.p_rhs;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, hsum = 0.0, hmax = 0.0;
+
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
+        const int matId = pr.materialId[i];
+        if (matId == EOS_TYPE_IGNORE || matId == BOUNDARY_PARTICLE_ID) {
+            /* BoundaryConditionsBeforeRHS, src/boundary.cu:98-145: deactivated particles are frozen */
+            p.vx[i] = 0.0;
+#if DIM > 1
+            p.vy[i] = 0.0;
+#endif
+#if DIM > 2
+            p.vz[i] = 0.0;
+#endif
+        }
+        if (matId >= 0 && matId != BOUNDARY_PARTICLE_ID) {
+            const MatParams &M = c_mat[matId];
+            if (p.rho[i] < M.density_floor) p.rho[i] = M.density_floor;
+            if (p.e && p.e[i] < M.energy_floor) p.e[i] = M.energy_floor;
+#if VARIABLE_SML
+            /* check_sml_boundary, src/tree.cu:930-952 */
+            const double smin = pr.h0[i] * M.f_sml_min, smax = pr.h0[i] * M.f_sml_max;
+            if (p.h[i] < smin) p.h[i] = smin;
+            else if (p.h[i] > smax) p.h[i] = smax;
+#endif
+        }
+        const double h = p.h[i];
+        hsum += h;
+        hmax = fmax(hmax, h);
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+            const double c = coord_of(p, i, a);
+            lo[a] = fmin(lo[a], c);
+            hi[a] = fmax(hi[a], c);
+        }
+    }
+
+    __shared__ double sh[PREP_THREADS / 32][PREP_VALUES];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double vals[PREP_VALUES];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        vals[a] = warp_min(lo[a]);
+        vals[3 + a] = warp_max(hi[a]);
+    }
+    vals[6] = warp_sum(hsum);
+    vals[7] = warp_max(hmax);
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < PREP_VALUES; k++) sh[warp][k] = vals[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < PREP_THREADS / 32; w++) {
+            for (int a = 0; a < 3; a++) {
+                sh[0][a] = fmin(sh[0][a], sh[w][a]);
+                sh[0][3 + a] = fmax(sh[0][3 + a], sh[w][3 + a]);
+            }
+            sh[0][6] += sh[w][6];
+            sh[0][7] = fmax(sh[0][7], sh[w][7]);
+        }
+        for (int k = 0; k < PREP_VALUES; k++) partials[blockIdx.x * PREP_VALUES + k] = sh[0][k];
+        __threadfence();
+        const unsigned int ticket = atomicAdd(counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+
+    /* last block: combine and set up the search grid */
+    __threadfence();
+    double r[PREP_VALUES];
+    for (int k = 0; k < PREP_VALUES; k++) r[k] = partials[k];
+    for (unsigned int b = 1; b < gridDim.x; b++) {
+        const volatile double *q = partials + b * PREP_VALUES;
+        for (int a = 0; a < 3; a++) {
+            r[a] = fmin(r[a], q[a]);
+            r[3 + a] = fmax(r[3 + a], q[3 + a]);
+        }
+        r[6] += q[6];
+        r[7] = fmax(r[7], q[7]);
+    }
+    *counter = 0;
+    Domain d;
+    for (int a = 0; a < 3; a++) {
+        d.lo[a] = (a < DIM) ? r[a] : 0.0;
+        d.hi[a] = (a < DIM) ? r[3 + a] : 0.0;
+    }
+    if (use_global) {
+        d.lo[0] = glo.x; d.lo[1] = glo.y; d.lo[2] = glo.z;
+        d.hi[0] = ghi.x; d.hi[1] = ghi.y; d.hi[2] = ghi.z;
+    }
+    /* root cube of the reference's octree (src/tree.cu:1071-1086) */
+    double radius = d.hi[0] - d.lo[0];
+#if DIM > 1
+    radius = fmax(d.hi[0] - d.lo[0], d.hi[1] - d.lo[1]);
+#endif
+#if DIM > 2
+    radius = fmax(radius, d.hi[2] - d.lo[2]);
+#endif
+    d.root_radius = 0.5 * radius;
+    for (int a = 0; a < 3; a++) d.root_centre[a] = 0.5 * (d.hi[a] + d.lo[a]);
+    d.h_max = r[7];
+    d.h_mean = r[6] / (double)v.n;
+#if VARIABLE_SML
+    double cell = fmin(d.h_max, 1.3 * d.h_mean) * 1.0001;
+#else
+    double cell = d.h_max * 1.0001;
+#endif
+    if (!(cell > 0.0)) cell = 1.0;
+    for (;;) {
+        double cells = 1.0;
+        for (int a = 0; a < 3; a++) {
+            d.nc[a] = (a < DIM) ? (int)floor((d.hi[a] - d.lo[a]) / cell) + 1 : 1;
+            cells *= (double)d.nc[a];
+        }
+        if (cells <= (double)max_cells) {
+            d.n_cells = d.nc[0] * d.nc[1] * d.nc[2];
+            break;
+        }
+        cell *= 1.26;
+    }
+    d.cell = cell;
+    d.cell_inv = 1.0 / cell;
+    *dom = d;
+}
+
+__device__ __forceinline__ int cell_coord(double x, double lo, double cell_inv, int nc)
+{
+    int c = (int)((x - lo) * cell_inv);
+    c = c < 0 ? 0 : c;
+    return c >= nc ? nc - 1 : c;
+}
+
+__global__ void k_cell_keys(b200sph_view v, const Domain *dom, int *keys, int *idx)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    const Domain &d = *dom;
+    int key = cell_coord(v.p.x[i], d.lo[0], d.cell_inv, d.nc[0]);
+#if DIM > 1
+    key += d.nc[0] * cell_coord(v.p.y[i], d.lo[1], d.cell_inv, d.nc[1]);
+#endif
+#if DIM > 2
+    key += d.nc[0] * d.nc[1] * cell_coord(v.p.z[i], d.lo[2], d.cell_inv, d.nc[2]);
+#endif
+    keys[i] = key;
+    idx[i] = i;
+}
+
+/* cell_start[c] = first sorted slot whose key >= c, for c in [0, n_cells] */
+__global__ void k_cell_start(const int *keys, int n, const Domain *dom, int *cell_start)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n) return;
+    const int n_cells = dom->n_cells;
+    const int prev = (s == 0) ? -1 : keys[s - 1];
+    const int cur = (s == n) ? n_cells : keys[s];
+    for (int c = prev + 1; c <= cur; c++) cell_start[c] = s;
+}
+
+__global__ void k_gather(b200sph_view v, Sorted s)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= s.n) return;
+    const int i = s.perm[k];
+    const b200sph_particle_arrays &p = v.p;
+    double4 a, b;
+    a.x = p.x[i]; b.x = p.vx[i];
+#if DIM > 1
+    a.y = p.y[i]; b.y = p.vy[i];
+#else
+    a.y = 0.0; b.y = 0.0;
+#endif
+#if DIM > 2
+    a.z = p.z[i]; b.z = p.vz[i];
+#else
+    a.z = 0.0; b.z = 0.0;
+#endif
+    a.w = p.h[i];
+    b.w = p.m[i];
+    s.pos4[k] = a;
+    s.vel4[k] = b;
+    s.mat[k] = v.p_rhs.materialId[i];
+}
+
+/* ------------------------------------------------------------------ k_neighbours
+ * Membership: d < h_i^2 && d < h_j^2, j != i, materialId[j] != IGNORE, with d accumulated as the
+ * reference's compiled code does (src/tree.cu:851-865: mul, then one fma per further axis). */
+__device__ __forceinline__ double pair_d2(const double4 &a, const double4 &b, double &dx, double &dy, double &dz)
+{
+    dx = a.x - b.x;
+    double d = __dmul_rn(dx, dx);
+#if DIM > 1
+    dy = a.y - b.y;
+    d = __fma_rn(dy, dy, d);
+#else
+    dy = 0.0;
+#endif
+#if DIM > 2
+    dz = a.z - b.z;
+    d = __fma_rn(dz, dz, d);
+#else
+    dz = 0.0;
+#endif
+    return d;
+}
+
+#define NBR_SLOT(s, k) ((((size_t)((s) / NBR_TILE)) * MAX_NUM_INTERACTIONS + (k)) * NBR_TILE + ((s) % NBR_TILE))
+
+__global__ void __launch_bounds__(128)
+k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_targets) return;
+    const Domain &d = *dom;
+    const double4 pi = s.pos4[k];
+    const double h2 = __dmul_rn(pi.w, pi.w);
+    const int reach = (int)(pi.w * d.cell_inv + 1e-9) + 1;
+    const int cx = cell_coord(pi.x, d.lo[0], d.cell_inv, d.nc[0]);
+    const int x0 = max(cx - reach, 0), x1 = min(cx + reach, d.nc[0] - 1);
+#if DIM > 1
+    const int cy = cell_coord(pi.y, d.lo[1], d.cell_inv, d.nc[1]);
+    const int y0 = max(cy - reach, 0), y1 = min(cy + reach, d.nc[1] - 1);
+#else
+    const int y0 = 0, y1 = 0;
+#endif
+#if DIM > 2
+    const int cz = cell_coord(pi.z, d.lo[2], d.cell_inv, d.nc[2]);
+    const int z0 = max(cz - reach, 0), z1 = min(cz + reach, d.nc[2] - 1);
+#else
+    const int z0 = 0, z1 = 0;
+#endif
+    int cnt = 0;
+    for (int z = z0; z <= z1; z++)
+        for (int y = y0; y <= y1; y++) {
+            const int row = d.nc[0] * (y + d.nc[1] * z);
+            const int jb = s.cell_start[row + x0], je = s.cell_start[row + x1 + 1];
+            for (int j = jb; j < je; j++) {
+                const double4 pj = s.pos4[j];
+                double dx, dy, dz;
+                const double dd = pair_d2(pi, pj, dx, dy, dz);
+                if (dd < h2 && dd < __dmul_rn(pj.w, pj.w) && j != k && s.mat[j] != EOS_TYPE_IGNORE) {
+                    if (cnt < MAX_NUM_INTERACTIONS) s.nbr[NBR_SLOT(k, cnt)] = j;
+                    cnt++;
+                }
+            }
+        }
+    if (cnt >= MAX_NUM_INTERACTIONS) { /* the reference asserts here (src/tree.cu:917) */
+        atomicMin(&flags[0], s.perm[k]);
+        cnt = MAX_NUM_INTERACTIONS - 1;
+    }
+    s.noi[k] = cnt;
+    atomicMax(&flags[1], cnt);
+}
+
+/* ------------------------------------------------------------------ k_density */
+__global__ void __launch_bounds__(128)
+k_density(Sorted s, b200sph_view v, double *rho_sorted, int n_targets)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_targets) return;
+    const int matId = s.mat[k];
+    const int i = s.perm[k];
+#if INTEGRATE_DENSITY
+    if (mat_ignored(matId) || c_mat[matId].density_via_kernel_sum < 1) {
+        rho_sorted[k] = v.p.rho[i];
+        return;
+    }
+#endif
+    const double4 pi = s.pos4[k];
+    const double hinv_i = 1.0 / pi.w;
+    double rho = s.vel4[k].w * cubic_spline_w(0.0, hinv_i);
+    if (!mat_ignored(matId)) {
+        const int noi = s.noi[k];
+        for (int q = 0; q < noi; q++) {
+            const int j = s.nbr[NBR_SLOT(k, q)];
+            if (mat_ignored(s.mat[j])) continue;
+            const double4 pj = s.pos4[j];
+            double dx, dy, dz, W, g;
+            const double r2 = pair_d2(pi, pj, dx, dy, dz);
+#if AVERAGE_KERNELS
+            /* W = (W(h_i) + W(h_j))/2.  The reference evaluates the second kernel with the
+             * smoothing length of the particle whose index equals the LOOP COUNTER
+             * (src/density.cu:130-138); identical whenever h is uniform, which holds for every
+             * config that sets AVERAGE_KERNELS (fixed sml per material). */
+            cubic_spline(r2, hinv_i, W, g);
+            if (pj.w != pi.w) {
+                double Wj;
+                cubic_spline(r2, 1.0 / pj.w, Wj, g);
+                W = 0.5 * (W + Wj);
+            }
+#elif VARIABLE_SML || INTEGRATE_SML
+            cubic_spline(r2, 1.0 / (0.5 * (pi.w + pj.w)), W, g);
+#else
+            cubic_spline(r2, hinv_i, W, g);
+#endif
+            rho = fma(s.vel4[j].w, W, rho);
+        }
+    }
+    rho_sorted[k] = rho;
+    v.p.rho[i] = rho;
+}
+
+/* ------------------------------------------------------------------ k_pointwise */
+__device__ inline double eos_soundspeed(const MatParams &M, double rho, double e, double p_old, double alpha_jutzi, double cs_in)
+{
+    const double limit = M.cs_limit;
+    switch (M.eos) {
+        case EOS_TYPE_POLYTROPIC_GAS: return sqrt(M.poly_K * pow(rho, M.poly_gamma - 1.0));
+        case EOS_TYPE_IDEAL_GAS: return sqrt(M.poly_gamma * p_old / rho);
+        case EOS_TYPE_ISOTHERMAL_GAS: return M.iso_cs;
+        case EOS_TYPE_MURNAGHAN: {
+            const double cs_sq = M.bulk / M.rho0 * pow(rho / M.rho0, M.n - 1.0);
+            return cs_sq < limit * limit ? limit : sqrt(cs_sq);
+        }
+        case EOS_TYPE_TILLOTSON: {
+            const double cs_sq = tillotson_cs2(M, rho, e, p_old);
+            return cs_sq < limit * limit ? limit : sqrt(cs_sq);
+        }
+        case EOS_TYPE_ANEOS: {
+            if (rho <= 0.0) return limit;
+            const TableCell c = aneos_locate(M, rho, e);
+            const double cs = c.ideal_gas ? sqrt(M.aneos_gamma * (M.aneos_gamma - 1.0) * e) : aneos_bilinear(M, c_aneos.cs, c);
+            return cs < limit ? limit : cs;
+        }
+#if PALPHA_POROSITY
+        case EOS_TYPE_JUTZI_MURNAGHAN:
+            if (M.pj_alpha_0 > 1.0) return M.cs_solid + (M.cs_porous - M.cs_solid) * (alpha_jutzi - 1.0) / (M.pj_alpha_0 - 1.0);
+            return M.cs_solid;
+        case EOS_TYPE_JUTZI_ANEOS: {
+            if (rho <= 0.0) return limit;
+            const TableCell c = aneos_locate(M, rho, e);
+            double cs = c.ideal_gas ? sqrt(M.aneos_gamma * (M.aneos_gamma - 1.0) * e) : aneos_bilinear(M, c_aneos.cs, c);
+            if (cs > M.cs_porous) cs = cs + (M.cs_porous - cs) * (alpha_jutzi - 1.0) / (M.pj_alpha_0 - 1.0);
+            return cs < limit ? limit : cs;
+        }
+        case EOS_TYPE_JUTZI: {
+            /* evaluated with the bulk density rho, not alpha*rho (src/soundspeed.cu:208-209) */
+            const double cs_sq = tillotson_cs2(M, rho, e, p_old);
+            if (cs_sq > M.cs_porous * M.cs_porous) {
+                double cs = sqrt(cs_sq);
+                if (M.pj_alpha_0 > 1.0) cs = cs + (M.cs_porous - cs) * (alpha_jutzi - 1.0) / (M.pj_alpha_0 - 1.0);
+                else cs = M.cs_solid;
+                return cs < limit ? limit : cs;
+            }
+            return cs_sq < limit * limit ? limit : sqrt(cs_sq);
+        }
+#endif
+        default: return cs_in; /* constant sound speed set by initializeSoundspeed */
+    }
+}
+
+struct PorousOut {
+    double dalphadp, dalphadrho, f, delpdelrho, delpdele, alpha;
+};
+
+__device__ inline double eos_pressure(const MatParams &M, double rho, double e, double cs, double alpha_in, PorousOut &po)
+{
+    (void)alpha_in; (void)po;
+    switch (M.eos) {
+        case EOS_TYPE_POLYTROPIC_GAS: return M.poly_K * pow(rho, M.poly_gamma);
+        case EOS_TYPE_IDEAL_GAS: return (M.poly_gamma - 1.0) * rho * e;
+        case EOS_TYPE_ISOTHERMAL_GAS: return cs * cs * rho;
+        case EOS_TYPE_MURNAGHAN: {
+            const double eta = rho / M.rho0;
+            return eta < M.rho_limit ? 0.0 : (M.bulk / M.n) * (pow(eta, M.n) - 1.0);
+        }
+        case EOS_TYPE_TILLOTSON: {
+            double d1, d2;
+            double pr = tillotson_p(M, rho, e, false, d1, d2);
+            if (e > 1e2 * M.till_Ecv && rho / M.till_rho0 < 1.0) pr = (M.poly_gamma - 1.0) * rho * e;
+            return pr;
+        }
+        case EOS_TYPE_ANEOS: {
+            if (rho <= 0.0) return 0.0;
+            const TableCell c = aneos_locate(M, rho, e);
+            return c.ideal_gas ? (M.aneos_gamma - 1.0) * rho * e : aneos_bilinear(M, c_aneos.p, c);
+        }
+#if PALPHA_POROSITY
+        case EOS_TYPE_JUTZI:
+        case EOS_TYPE_JUTZI_MURNAGHAN: {
+            /* p = p_solid(alpha rho, e) / alpha with the crush curve alpha(p), src/pressure.cu:204-449 */
+            const double al = alpha_in;
+            double psolid;
+            if (M.eos == EOS_TYPE_JUTZI) {
+                psolid = tillotson_p(M, rho * al, e, true, po.delpdele, po.delpdelrho);
+            } else {
+                const double eta = rho * al / M.rho0;
+                po.delpdele = 0.0;
+                if (eta < M.rho_limit) {
+                    psolid = 0.0;
+                    po.delpdelrho = 0.0;
+                } else {
+                    psolid = M.bulk / M.n * (pow(eta, M.n) - 1.0);
+                    po.delpdelrho = M.bulk / M.rho0 * pow(eta, M.n - 1.0);
+                }
+            }
+            const double pr = psolid / al;
+            const double p_e = M.pj_p_elastic, p_t = M.pj_p_transition, p_s = M.pj_p_compacted, a0 = M.pj_alpha_0;
+            double dadp = 0.0;
+            if (M.crushcurve_style == 0) {
+                if (pr > p_e && pr < p_s) dadp = -2.0 * (a0 - 1.0) * (p_s - pr) / sq(p_s - p_e);
+            } else if (M.crushcurve_style == 1) {
+                const double k = (a0 - 1.0) / (M.pj_alpha_e - 1.0);
+                if (pr > p_e && pr < p_t)
+                    dadp = -k * (M.pj_alpha_e - M.pj_alpha_t) * M.pj_n1 * (pow(p_t - pr, M.pj_n1 - 1.0) / pow(p_t - p_e, M.pj_n1)) -
+                           k * (M.pj_alpha_t - 1.0) * M.pj_n2 * (pow(p_s - pr, M.pj_n2 - 1.0) / pow(p_s - p_e, M.pj_n2));
+                else if (pr >= p_t && pr < p_s)
+                    dadp = -k * (M.pj_alpha_t - 1.0) * M.pj_n2 * (pow(p_s - pr, M.pj_n2 - 1.0) / pow(p_s - p_e, M.pj_n2));
+            }
+            po.dalphadp = dadp;
+            po.dalphadrho = ((pr / (rho * rho) * po.delpdele + al * po.delpdelrho) * dadp) / (al + dadp * (pr - rho * po.delpdelrho));
+            po.f = 1.0 + po.dalphadrho * rho / al;
+            po.alpha = al;
+            if (al <= 1.0) {
+                po.f = 1.0;
+                po.alpha = 1.0;
+                po.dalphadp = 0.0;
+                po.dalphadrho = 0.0;
+            }
+            return pr;
+        }
+#endif
+        default: return 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sorted)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= s.n) return;
+    const int i = s.perm[k];
+    const int matId = s.mat[k];
+    const b200sph_particle_arrays &p = v.p;
+    const b200sph_particle_arrays &pr = v.p_rhs;
+    const double m = s.vel4[k].w;
+    double rho = use_rho_sorted ? rho_sorted[k] : p.rho[i];
+
+    if (matId < 0) { /* deactivated particle: never a neighbour, keep the records finite */
+        s.gas4[k] = make_double4(0.0, 0.0, rho, 0.0);
+        return;
+    }
+    const MatParams &M = c_mat[matId];
+    const double e = p.e ? p.e[i] : 0.0;
+#if PALPHA_POROSITY
+    const double alpha_in = p.alpha_jutzi[i];
+#else
+    const double alpha_in = 1.0;
+#endif
+    /* sound speed first, with the pressure left by the previous call (src/rhs.cu:398 before :458) */
+    const double cs = eos_soundspeed(M, rho, e, p.p[i], alpha_in, p.cs[i]);
+    p.cs[i] = cs;
+    if (M.eos == EOS_TYPE_IGNORE) {
+        s.gas4[k] = make_double4(0.0, cs, rho, m / rho);
+        return;
+    }
+    PorousOut po;
+    double pres = eos_pressure(M, rho, e, cs, alpha_in, po);
+#if PALPHA_POROSITY
+    if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN) {
+        p.dalphadp[i] = po.dalphadp;
+        p.dalphadrho[i] = po.dalphadrho;
+        p.f[i] = po.f;
+        p.delpdelrho[i] = po.delpdelrho;
+        p.delpdele[i] = po.delpdele;
+        if (alpha_in <= 1.0) p.alpha_jutzi[i] = 1.0;
+    } else {
+        p.alpha_jutzi_old[i] = alpha_in;
+    }
+#endif
+#if REAL_HYDRO
+    if (pres < 0.0) pres = 0.0;
+#endif
+
+#if SOLID
+    double S[DIM][DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) S[a][b] = p.S[(size_t)i * DD + a * DIM + b];
+#if FRAGMENTATION || B200_PLASTICITY
+    /* symmetrizeStress, src/timeintegration.cu:116-130 */
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < a; b++) {
+            const double val = 0.5 * (S[a][b] + S[b][a]);
+            S[a][b] = val;
+            S[b][a] = val;
+        }
+#endif
+#if FRAGMENTATION
+    /* damageLimit, src/damage.cu:33-82 */
+    double damage;
+    {
+        double dmg = p.d[i], dmg_max = 1.0;
+        const int nof = p.numFlaws[i], noaf = p.numActiveFlaws[i];
+        if (dmg < 0.0) dmg = 0.0;
+        if (nof > 0) dmg_max = pow((double)noaf / (double)nof, 1.0 / DIM);
+        if (dmg > dmg_max) dmg = dmg_max;
+        p.d[i] = dmg;
+#if PALPHA_POROSITY
+        double dpor = p.damage_porjutzi[i];
+        if (dpor > 1.0) { dpor = 1.0; p.damage_porjutzi[i] = 1.0; }
+        else if (dpor < 0.0) { dpor = 0.0; p.damage_porjutzi[i] = 0.0; }
+        damage = pow(dmg, (double)DIM) + pow(dpor, (double)DIM);
+        if (damage > 1.0) damage = 1.0;
+#else
+        damage = pow(dmg, (double)DIM);
+#endif
+        p.damage_total[i] = damage;
+        if (damage > 1.0) damage = 1.0;
+        if (damage < 0.0) damage = 0.0;
+    }
+#endif
+#if B200_PLASTICITY
+    /* plasticityModel, src/plasticity.cu:117-388 */
+    {
+        double J2 = 0.0, mises_f = 1.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) J2 = fma(S[a][b], S[a][b], J2);
+        J2 *= 0.5;
+#if COLLINS_PLASTICITY
+        const double y_0 = M.cohesion, y_M = M.yield_stress, mu_i = M.friction;
+        double y_i = y_0, y;
+        if (pres > 0.0) y_i += mu_i * pres / (1.0 + mu_i * pres / (y_M - y_0));
+#if COLLINS_PLASTICITY_INCLUDE_MELT_ENERGY
+        if (e >= M.melt_energy) y_i = 0.0;
+        else if (e > 0.0) y_i *= (1.0 - e / M.melt_energy);
+#endif
+#if FRAGMENTATION
+        {
+            const double y_0_d = M.cohesion_damaged;
+            double y_d;
+            if (pres > 0.0) y_d = y_0_d + M.friction_damaged * pres;
+            else if (pres > -y_0_d) y_d = y_0_d + pres;
+            else y_d = 0.0;
+            if (y_d < 0.0) y_d = 0.0;
+            y = (1.0 - damage) * y_i + damage * y_d;
+            if (y > y_i) y = y_i;
+            /* cap on negative pressure release by damage (applied once, here) */
+            if (pres < -y_0_d) pres = ((1.0 - damage) * pres > -y_0_d) ? -y_0_d : (1.0 - damage) * pres;
+        }
+#else
+        y = y_i;
+#endif
+        if (J2 > 0.0) mises_f = y / sqrt(J2);
+#else /* VON_MISES_PLASTICITY */
+        if (J2 > 0.0) mises_f = M.yield_stress * M.yield_stress / (3.0 * J2);
+#endif
+        mises_f = fmin(mises_f, 1.0);
+        if (mises_f < 0.0) mises_f = 0.0;
+        pr.plastic_f[i] = mises_f;
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) S[a][b] *= mises_f;
+    }
+#endif
+#if FRAGMENTATION || B200_PLASTICITY
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) p.S[(size_t)i * DD + a * DIM + b] = S[a][b];
+#endif
+    /* set_stress_tensor, src/stress.cu:50-157 */
+    double ptmp = pres;
+#if !COLLINS_PLASTICITY && FRAGMENTATION
+    if (pres < 0.0) ptmp = (1.0 - damage) * pres;
+#endif
+    const double irho2 = 1.0 / (rho * rho);
+    double sigma[DIM][DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+#if FRAGMENTATION && DAMAGE_ACTS_ON_S
+            double sg = (1.0 - damage) * S[a][b];
+#else
+            double sg = S[a][b];
+#endif
+            if (a == b) sg -= ptmp;
+            sigma[a][b] = sg;
+            pr.sigma[(size_t)i * DD + a * DIM + b] = sg;
+            s.sig[(size_t)k * DD + a * DIM + b] = sg * irho2;
+        }
+#if ARTIFICIAL_STRESS
+    /* compute_artificial_stress, src/artificial_stress.cu:34-100: R = -eps * sigma_+ in principal axes */
+    {
+        double ev[DIM], V[DIM][DIM];
+        sym_eigen(sigma, ev, V);
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) {
+                double r = 0.0;
+#pragma unroll
+                for (int c = 0; c < DIM; c++) {
+                    const double rc = ev[c] > 0.0 ? -M.epsilon_stress * ev[c] : 0.0;
+                    /* R = V^T diag V as the reference multiplies (rotation^T * (diag * rotation)) */
+                    r += V[c][a] * rc * V[c][b];
+                }
+                pr.R[(size_t)i * DD + a * DIM + b] = r;
+                s.rart[(size_t)k * DD + a * DIM + b] = r * irho2;
+            }
+    }
+#endif
+    p.p[i] = pres;
+    s.gas4[k] = make_double4(irho2, cs, rho, m / rho);
+#else /* HYDRO */
+    p.p[i] = pres;
+    s.gas4[k] = make_double4(pres / (rho * rho), cs, rho, m / rho);
+#endif
+}
+
+#if TENSORIAL_CORRECTION
+/* ------------------------------------------------------------------ k_correction */
+__global__ void __launch_bounds__(128)
+k_correction(Sorted s, b200sph_view v, int n_targets)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_targets) return;
+    const int i = s.perm[k];
+    double C[DIM][DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) C[a][b] = (a == b) ? 1.0 : 0.0;
+    if (!mat_ignored(s.mat[k])) {
+        const double4 pi = s.pos4[k];
+        const double hinv = 1.0 / pi.w;   /* h_i, not the pair mean (src/kernel.cu:637) */
+        double A[DIM][DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) A[a][b] = 0.0;
+        const int noi = s.noi[k];
+        for (int q = 0; q < noi; q++) {
+            const int j = s.nbr[NBR_SLOT(k, q)];
+            if (mat_ignored(s.mat[j])) continue;
+            const double4 pj = s.pos4[j];
+            double dr[3], W, g;
+            const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
+#if AVERAGE_KERNELS
+            cubic_spline(r2, hinv, W, g);
+            if (pj.w != pi.w) {
+                double Wj, gj;
+                cubic_spline(r2, 1.0 / pj.w, Wj, gj);
+                g = 0.5 * (g + gj);
+            }
+#else
+            cubic_spline(r2, hinv, W, g);
+#endif
+            const double w = s.gas4[j].w * g;   /* (m_j/rho_j) * dW/dr / r */
+#pragma unroll
+            for (int a = 0; a < DIM; a++)
+#pragma unroll
+                for (int b = 0; b < DIM; b++) A[a][b] = fma(-w * dr[a], dr[b], A[a][b]);
+        }
+        sym_pinv(A, C);
+#if DIM == 2
+        const double det = C[0][0] * C[1][1] - C[0][1] * C[1][0];
+#else
+        const double det = C[0][0] * (C[1][1] * C[2][2] - C[1][2] * C[2][1]) - C[0][1] * (C[1][0] * C[2][2] - C[1][2] * C[2][0]) +
+                           C[0][2] * (C[1][0] * C[2][1] - C[1][1] * C[2][0]);
+#endif
+        double max_entry = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) max_entry = fmax(max_entry, fabs(C[a][b]));
+        if (fabs(det) < 0.2 || fabs(det) > 5.0 || max_entry > 5.0) {
+#pragma unroll
+            for (int a = 0; a < DIM; a++)
+#pragma unroll
+                for (int b = 0; b < DIM; b++) C[a][b] = (a == b) ? 1.0 : 0.0;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+            s.cmat[(size_t)k * DD + a * DIM + b] = C[a][b];
+            v.p_rhs.tensorialCorrectionMatrix[(size_t)i * DD + a * DIM + b] = C[a][b];
+        }
+}
+#endif
+
+/* ------------------------------------------------------------------ k_forces */
+__global__ void __launch_bounds__(128)
+k_forces(Sorted s, b200sph_view v, int n_targets)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_targets) return;
+    const int i = s.perm[k];
+    const int matId = s.mat[k];
+    const b200sph_particle_arrays &p = v.p;
+    const b200sph_particle_arrays &pr = v.p_rhs;
+    const double4 pi = s.pos4[k];
+    const double4 vi = s.vel4[k];
+    const int noi = s.noi[k];
+    p.noi[i] = noi;
+
+    const bool active = !(matId == BOUNDARY_PARTICLE_ID || mat_ignored(matId)) && i < v.n_real;
+    double acc[3] = {0.0, 0.0, 0.0}, drhodt = 0.0, dedt = 0.0, dhdt = 0.0, muijmax = 0.0;
+    (void)dedt; (void)dhdt; (void)muijmax;
+#if SOLID
+    double edot[DIM][DIM], rdot[DIM][DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) edot[a][b] = rdot[a][b] = 0.0;
+    double sig_i[DIM][DIM];
+#if TENSORIAL_CORRECTION
+    double Ci[DIM][DIM];
+#endif
+#if ARTIFICIAL_STRESS
+    double Ri[DIM][DIM];
+#endif
+#endif
+
+    if (active && noi > 0) {
+        const MatParams &M = c_mat[matId];
+        const double4 gi = s.gas4[k];
+        const double rho_i = gi.z;
+        (void)rho_i;
+#if ARTIFICIAL_VISCOSITY
+        const double av_alpha = M.av_alpha, av_beta = M.av_beta;
+#endif
+#if SOLID
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) {
+                sig_i[a][b] = s.sig[(size_t)k * DD + a * DIM + b];
+#if TENSORIAL_CORRECTION
+                Ci[a][b] = s.cmat[(size_t)k * DD + a * DIM + b];
+#endif
+#if ARTIFICIAL_STRESS
+                Ri[a][b] = s.rart[(size_t)k * DD + a * DIM + b];
+#endif
+            }
+        const double m_over_rho_i_unit = 1.0 / rho_i;   /* strain rate uses m_j / rho_i (src/internal_forces.cu:476) */
+#endif
+#if !(VARIABLE_SML || INTEGRATE_SML)
+        const double hinv_fixed = 1.0 / pi.w;
+#endif
+#if ARTIFICIAL_STRESS
+        const double w_ref_dist = M.mean_particle_distance;
+#endif
+        for (int q = 0; q < noi; q++) {
+            const int j = s.nbr[NBR_SLOT(k, q)];
+            if (mat_ignored(s.mat[j])) continue;
+            const double4 pj = s.pos4[j];
+            const double4 vj = s.vel4[j];
+            const double4 gj = s.gas4[j];
+            double dr[3], dv[3], W, g;
+            const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
+            dv[0] = vi.x - vj.x; dv[1] = vi.y - vj.y; dv[2] = vi.z - vj.z;
+#if VARIABLE_SML || INTEGRATE_SML
+            const double hbar = 0.5 * (pi.w + pj.w);
+            const double hinv = 1.0 / hbar;
+#else
+            /* fixed h; with AVERAGE_KERNELS and no SHEPARD_CORRECTION the reference also uses h_i
+             * only (the averaging lines are compiled out, src/internal_forces.cu:328-346) */
+            const double hinv = hinv_fixed;
+#endif
+            cubic_spline(r2, hinv, W, g);
+            double gw[DIM];   /* plain kernel gradient */
+#pragma unroll
+            for (int a = 0; a < DIM; a++) gw[a] = g * dr[a];
+            const double mj = vj.w;
+
+#if TENSORIAL_CORRECTION
+            double gci[DIM], gcj[DIM], gsym[DIM];
+#pragma unroll
+            for (int a = 0; a < DIM; a++) {
+                double ti = 0.0, tj = 0.0;
+#pragma unroll
+                for (int b = 0; b < DIM; b++) {
+                    ti = fma(Ci[a][b], gw[b], ti);
+                    tj = fma(s.cmat[(size_t)j * DD + a * DIM + b], gw[b], tj);
+                }
+                gci[a] = ti;
+                gcj[a] = tj;
+                gsym[a] = 0.5 * (ti + tj);
+            }
+#else
+            const double *gsym = gw;
+#endif
+            double vvnablaW = 0.0;
+#pragma unroll
+            for (int a = 0; a < DIM; a++) vvnablaW = fma(dv[a], gsym[a], vvnablaW);
+
+#if SOLID
+            /* strain rate and rotation rate, edot_ab = 1/2 (d_b v_a + d_a v_b) */
+            {
+                const double w = -0.5 * mj * m_over_rho_i_unit;
+#pragma unroll
+                for (int a = 0; a < DIM; a++)
+#pragma unroll
+                    for (int b = 0; b < DIM; b++) {
+                        const double t1 = dv[a] * gsym[b], t2 = dv[b] * gsym[a];
+                        edot[a][b] = fma(w, t1 + t2, edot[a][b]);
+                        rdot[a][b] = fma(w, t1 - t2, rdot[a][b]);
+                    }
+            }
+#endif
+            double pij = 0.0;
+#if ARTIFICIAL_VISCOSITY
+            {
+                double vr = 0.0;
+#pragma unroll
+                for (int a = 0; a < DIM; a++) vr = fma(dv[a], dr[a], vr);
+                if (vr < 0.0) {
+                    const double csbar = 0.5 * (gi.y + gj.y);
+                    const double smooth = 0.5 * (pi.w + pj.w);
+                    const double mu = smooth * vr / (r2 + smooth * smooth * 1e-2);
+                    muijmax = fmax(muijmax, mu);
+                    const double rhobar = 0.5 * (gi.z + gj.z);
+                    pij = (av_beta * mu - av_alpha * csbar) * mu / rhobar;
+                }
+            }
+#endif
+#if SOLID
+            {
+                double aj[DIM];
+#pragma unroll
+                for (int a = 0; a < DIM; a++) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int b = 0; b < DIM; b++) {
+#if TENSORIAL_CORRECTION
+                        t = fma(s.sig[(size_t)j * DD + a * DIM + b], gcj[b], t);
+                        t = fma(sig_i[a][b], gci[b], t);
+#else
+                        t = fma(s.sig[(size_t)j * DD + a * DIM + b] + sig_i[a][b], gw[b], t);
+#endif
+                    }
+                    aj[a] = mj * t;
+                }
+#if ARTIFICIAL_STRESS
+                /* Monaghan (2000) tensile-instability fix: (W(r)/W(dp))^n * (R_i/rho_i^2 + R_j/rho_j^2) */
+                {
+                    const double hb = 0.5 * (pi.w + pj.w), hbinv = 1.0 / hb;
+                    const double r = sqrt(r2);
+                    const double ratio = cubic_spline_w(r, hbinv) / cubic_spline_w(w_ref_dist, hbinv);
+                    const double artf = pow(ratio, M.exponent_tensor);
+#pragma unroll
+                    for (int a = 0; a < DIM; a++) {
+                        double t = 0.0;
+#pragma unroll
+                        for (int b = 0; b < DIM; b++) {
+#if TENSORIAL_CORRECTION
+                            t = fma(Ri[a][b], gci[b], t);
+                            t = fma(s.rart[(size_t)j * DD + a * DIM + b], gcj[b], t);
+#else
+                            t = fma(Ri[a][b] + s.rart[(size_t)j * DD + a * DIM + b], gw[b], t);
+#endif
+                        }
+                        const double art = mj * artf * t;
+                        acc[a] += art;
+#if INTEGRATE_ENERGY && TENSORIAL_CORRECTION
+                        dedt = fma(-0.5 * art, dv[a], dedt);
+#endif
+                    }
+                }
+#endif
+#pragma unroll
+                for (int a = 0; a < DIM; a++) acc[a] += aj[a];
+#if INTEGRATE_ENERGY
+                /* pairwise-conservative heating: 1/2 m_j (sigma_i/rho_i^2 grad_i + sigma_j/rho_j^2 grad_j) . dv */
+                {
+                    double t = 0.0;
+#pragma unroll
+                    for (int a = 0; a < DIM; a++) t = fma(aj[a], dv[a], t);
+                    dedt = fma(0.5, t, dedt);
+                }
+#endif
+            }
+#else /* HYDRO */
+            {
+                const double w = -mj * (gi.x + gj.x);
+                double t = 0.0;
+#pragma unroll
+                for (int a = 0; a < DIM; a++) {
+                    const double aj = w * gw[a];
+                    acc[a] += aj;
+                    t = fma(aj, dv[a], t);
+                }
+#if INTEGRATE_ENERGY
+                dedt = fma(-0.5, t, dedt);
+#endif
+            }
+#endif
+#if ARTIFICIAL_VISCOSITY
+            {
+                const double w = -mj * pij;
+#pragma unroll
+                for (int a = 0; a < DIM; a++) acc[a] = fma(w, gsym[a], acc[a]);
+#if INTEGRATE_ENERGY
+                if (!v.is_relaxation_run) dedt = fma(0.5 * mj * pij, vvnablaW, dedt);
+#endif
+            }
+#endif
+            drhodt = fma(gi.z * gj.w, vvnablaW, drhodt);            /* rho_i/rho_j m_j v.gradW */
+#if INTEGRATE_SML
+            dhdt = fma(-(1.0 / DIM) * pi.w * gj.w, vvnablaW, dhdt);
+#endif
+        }
+    }
+
+    /* ---------------- per-particle epilogue: everything the integrators read, in caller order */
+    if (!active) {
+        /* zero_all_derivatives + boundary hooks for deactivated / virtual particles */
+        p.ax[i] = 0.0; p.dxdt[i] = 0.0;
+#if DIM > 1
+        p.ay[i] = 0.0; p.dydt[i] = 0.0;
+#endif
+#if DIM > 2
+        p.az[i] = 0.0; p.dzdt[i] = 0.0;
+#endif
+        p.drhodt[i] = 0.0;
+#if INTEGRATE_ENERGY
+        p.dedt[i] = 0.0;
+#endif
+#if INTEGRATE_SML
+        p.dhdt[i] = 0.0;
+#endif
+#if SOLID
+#pragma unroll
+        for (int a = 0; a < DD; a++) p.dSdt[(size_t)i * DD + a] = 0.0;
+#endif
+#if FRAGMENTATION
+        p.dddt[i] = 0.0;
+#endif
+        return;
+    }
+
+    const MatParams &M = c_mat[matId];
+    p.ax[i] = acc[0]; p.dxdt[i] = vi.x;
+#if DIM > 1
+    p.ay[i] = acc[1]; p.dydt[i] = vi.y;
+#endif
+#if DIM > 2
+    p.az[i] = acc[2]; p.dzdt[i] = vi.z;
+#endif
+#if INTEGRATE_DENSITY
+    if (M.density_via_kernel_sum) drhodt = 0.0;
+#endif
+    /* BoundaryConditionsAfterRHS floors (src/boundary.cu:311-324) act on the stored rate only */
+    if (s.gas4[k].z < M.density_floor) {
+        p.rho[i] = M.density_floor;
+        p.drhodt[i] = 0.0;
+    } else {
+        p.drhodt[i] = drhodt;
+    }
+#if INTEGRATE_ENERGY
+    p.dedt[i] = dedt;
+#endif
+#if INTEGRATE_SML
+    p.dhdt[i] = dhdt;
+#endif
+#if PALPHA_POROSITY
+    double dalphadt = 0.0, alpha_now = p.alpha_jutzi[i];
+    if (noi > 0 && (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN || M.eos == EOS_TYPE_JUTZI_ANEOS)) {
+        if (alpha_now <= 1.0) {
+            alpha_now = 1.0;
+            p.alpha_jutzi[i] = 1.0;
+        } else {
+            const double dadp = p.dalphadp[i], dpdr = p.delpdelrho[i];
+#if INTEGRATE_ENERGY
+            dalphadt = ((dedt * p.delpdele[i] + alpha_now * drhodt * dpdr) * dadp) / (alpha_now + dadp * (p.p[i] - s.gas4[k].z * dpdr));
+#else
+            dalphadt = ((alpha_now * drhodt * dpdr) * dadp) / (alpha_now + dadp * (p.p[i] - s.gas4[k].z * dpdr));
+#endif
+            if (dalphadt > 0.0) dalphadt = 0.0;
+        }
+    }
+    p.dalphadt[i] = dalphadt;
+#endif
+#if SOLID
+    if (noi < 1) {
+#pragma unroll
+        for (int a = 0; a < DD; a++) p.dSdt[(size_t)i * DD + a] = 0.0;
+#if FRAGMENTATION
+        p.dddt[i] = 0.0;
+#if PALPHA_POROSITY
+        p.ddamage_porjutzidt[i] = 0.0;
+#endif
+#endif
+        return;
+    }
+    {
+        const double shear = M.shear, bulk = M.bulk, young = M.young;
+        (void)bulk;
+        double S[DIM][DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) S[a][b] = p.S[(size_t)i * DD + a * DIM + b];
+        double tr = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) tr += edot[a][a];
+        const double pf = 1.0 - pr.plastic_f[i];
+        double K2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) {
+                /* Hooke + Jaumann rotation terms (src/internal_forces.cu:1028-1050) */
+                double ds = 2.0 * shear * edot[a][b];
+                double ep = pf * edot[a][b];
+                if (a == b) {
+                    ds -= 2.0 * shear * tr / 3.0;
+                    ep -= pf * tr / 3.0;
+                }
+#pragma unroll
+                for (int c = 0; c < DIM; c++) {
+                    ds = fma(S[a][c], rdot[b][c], ds);
+                    ds = fma(S[b][c], rdot[a][c], ds);
+                }
+#if PALPHA_POROSITY && STRESS_PALPHA_POROSITY
+                if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN || M.eos == EOS_TYPE_JUTZI_ANEOS)
+                    ds = p.f[i] / alpha_now * ds - 1.0 / (alpha_now * alpha_now) * S[a][b] * dalphadt;
+#endif
+                p.dSdt[(size_t)i * DD + a * DIM + b] = ds;
+                K2 = fma(ep, ep, K2);
+            }
+        p.edotp[i] = sqrt(2.0 / 3.0 * K2);
+#if ARTIFICIAL_VISCOSITY
+        p.muijmax[i] = muijmax;
+#endif
+        /* largest principal stress -> local scalar strain (Grady-Kipp) */
+        double sigma[DIM][DIM];
+        const double rho2 = s.gas4[k].z * s.gas4[k].z;
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) sigma[a][b] = pr.sigma[(size_t)i * DD + a * DIM + b];
+        (void)rho2;
+        const double tensile_max = sym_max_eigenvalue(sigma);
+        double local_strain = tensile_max / young;
+#if FRAGMENTATION
+        {
+            const double di_tensile = pow(p.d[i], (double)DIM);
+            if (di_tensile < 1.0) {
+                local_strain = tensile_max / ((1.0 - di_tensile) * young);
+                const double c_g = 0.4 * sqrt((bulk + 4.0 * shear * (1.0 - di_tensile) / 3.0) / s.gas4[k].z);
+                int n_active = 0;
+                const int nf = p.numFlaws[i];
+                const double *fl = pr.flaws + (size_t)i * v.max_num_flaws;
+                for (int f = 0; f < nf; f++) n_active += (fl[f] < local_strain) ? 1 : 0;
+                p.numActiveFlaws[i] = max(n_active, p.numActiveFlaws[i]);
+                p.dddt[i] = n_active * c_g / pi.w;
+            } else {
+                local_strain = 0.0;
+                p.numActiveFlaws[i] = p.numFlaws[i];
+                p.dddt[i] = 0.0;
+                p.d[i] = 1.0;
+            }
+#if PALPHA_POROSITY
+            double ddp = 0.0;
+            if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN || M.eos == EOS_TYPE_JUTZI_ANEOS) {
+                const double deld = 0.01, a0 = M.pj_alpha_0;
+                if (a0 > 1.0)
+                    ddp = -1.0 / DIM * pow(1.0 - (alpha_now - 1.0) / (a0 - 1.0) + deld, 1.0 / DIM - 1.0) /
+                          (pow(1.0 + deld, 1.0 / DIM) - pow(deld, 1.0 / DIM)) * 1.0 / (a0 - 1.0) * dalphadt;
+            }
+            p.ddamage_porjutzidt[i] = ddp;
+#endif
+        }
+#endif
+        p.local_strain[i] = local_strain;
+    }
+#endif /* SOLID */
+}
+
+/* ------------------------------------------------------------------ export of neighbour lists */
+__global__ void k_export_interactions(Sorted s, int *out, int max_per_row)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= s.n) return;
+    const int i = s.perm[k];
+    const int noi = s.noi[k];
+    int *row = out + (size_t)i * max_per_row;
+    for (int q = 0; q < max_per_row; q++) row[q] = (q < noi) ? s.perm[s.nbr[NBR_SLOT(k, q)]] : -1;
+}
+
+/* cold calls */
+__global__ void k_pressure_only(b200sph_view v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    const int matId = v.p_rhs.materialId[i];
+    if (matId < 0 || c_mat[matId].eos == EOS_TYPE_IGNORE) return;
+    const MatParams &M = c_mat[matId];
+    const b200sph_particle_arrays &p = v.p;
+#if PALPHA_POROSITY
+    const double alpha_in = p.alpha_jutzi[i];
+#else
+    const double alpha_in = 1.0;
+#endif
+    PorousOut po;
+    double pres = eos_pressure(M, p.rho[i], p.e ? p.e[i] : 0.0, p.cs[i], alpha_in, po);
+#if PALPHA_POROSITY
+    if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN) {
+        p.dalphadp[i] = po.dalphadp;
+        p.dalphadrho[i] = po.dalphadrho;
+        p.f[i] = po.f;
+        p.delpdelrho[i] = po.delpdelrho;
+        p.delpdele[i] = po.delpdele;
+        if (alpha_in <= 1.0) p.alpha_jutzi[i] = 1.0;
+    } else {
+        p.alpha_jutzi_old[i] = alpha_in;
+    }
+#endif
+#if REAL_HYDRO
+    if (pres < 0.0) pres = 0.0;
+#endif
+    p.p[i] = pres;
+}
+
+__global__ void k_init_soundspeed(b200sph_view v)
+{
+    /* initializeSoundspeed, src/soundspeed.cu:292-322 */
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    const int matId = v.p_rhs.materialId[i];
+    if (matId < 0) return;
+    const MatParams &M = c_mat[matId];
+    double *cs = v.p.cs;
+    switch (M.eos) {
+        case EOS_TYPE_POLYTROPIC_GAS: cs[i] = 0.0; break;
+        case EOS_TYPE_ISOTHERMAL_GAS: cs[i] = 203.0; break;
+        case EOS_TYPE_TILLOTSON: cs[i] = sqrt(M.bulk / M.till_rho0); break;
+        case EOS_TYPE_ANEOS: cs[i] = M.aneos_bulk_cs; break;
+        case EOS_TYPE_MURNAGHAN: cs[i] = sqrt(M.bulk / M.rho0); break;
+        case EOS_TYPE_JUTZI: case EOS_TYPE_JUTZI_ANEOS: case EOS_TYPE_JUTZI_MURNAGHAN: cs[i] = M.cs_porous; break;
+        case EOS_TYPE_REGOLITH: cs[i] = 500.0; break;
+        default: break;
+    }
+}
+
+#if FRAGMENTATION
+__global__ void k_damage_limit(b200sph_view v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    const int matId = v.p_rhs.materialId[i];
+    if (mat_ignored(matId)) return;
+    const b200sph_particle_arrays &p = v.p;
+    double dmg = p.d[i], dmg_max = 1.0;
+    const int nof = p.numFlaws[i], noaf = p.numActiveFlaws[i];
+    if (dmg < 0.0) dmg = 0.0;
+    if (nof > 0) dmg_max = pow((double)noaf / (double)nof, 1.0 / DIM);
+    if (dmg > dmg_max) dmg = dmg_max;
+    p.d[i] = dmg;
+#if PALPHA_POROSITY
+    double dpor = p.damage_porjutzi[i];
+    if (dpor > 1.0) { dpor = 1.0; p.damage_porjutzi[i] = 1.0; }
+    else if (dpor < 0.0) { dpor = 0.0; p.damage_porjutzi[i] = 0.0; }
+    double tot = pow(dmg, (double)DIM) + pow(dpor, (double)DIM);
+    if (tot > 1.0) tot = 1.0;
+    p.damage_total[i] = tot;
+#else
+    p.damage_total[i] = pow(dmg, (double)DIM);
+#endif
+}
+#endif
+
+/* ------------------------------------------------------------------ host orchestration */
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            snprintf(h->err, sizeof(h->err), "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return B200SPH_ERR_CUDA;                                                                 \
+        }                                                                                            \
+    } while (0)
+
+static inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; }
+
+int gravity_tree_create(b200sph_handle *h);
+void gravity_tree_destroy(b200sph_handle *h);
+int gravity_eval(b200sph_handle *h, const b200sph_view &v, int *launches);
+
+extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int *offender)
+{
+    if (!h || !view) return B200SPH_ERR_BAD_ARGUMENT;
+    const b200sph_view &v = *view;
+    if (v.n <= 0 || v.n > h->n_max) {
+        snprintf(h->err, sizeof(h->err), "n = %d outside (0, n_max = %d]", v.n, h->n_max);
+        return B200SPH_ERR_BAD_ARGUMENT;
+    }
+    if (!h->materials_set) {
+        snprintf(h->err, sizeof(h->err), "b200sph_set_materials() has not been called");
+        return B200SPH_ERR_BAD_ARGUMENT;
+    }
+    if (!v.p.x || !v.p.vx || !v.p.m || !v.p.h || !v.p.rho || !v.p.p || !v.p.cs || !v.p.ax || !v.p.dxdt || !v.p.drhodt ||
+        !v.p.noi || !v.p_rhs.materialId) {
+        snprintf(h->err, sizeof(h->err), "view is missing a mandatory array (x, vx, m, h, rho, p, cs, ax, dxdt, drhodt, noi, materialId)");
+        return B200SPH_ERR_BAD_ARGUMENT;
+    }
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Sorted &s = h->s;
+    s.n = v.n;
+    const int n = v.n;
+    const int n_targets = (h->n_owned > 0 && h->n_owned < n) ? n : n; /* halo particles also need lists (rho, C) */
+    int launches = 0;
+    const int T = 128;
+
+    CU(cudaEventRecord(h->ev[0], st));
+    int init_flags[4] = {0x7fffffff, 0, 0, 0};
+    CU(cudaMemcpyAsync(h->d_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
+    {
+        const int blocks = min(blocks_for(n, PREP_THREADS), 148 * 4);
+        double3 glo = make_double3(h->global_lo[0], h->global_lo[1], h->global_lo[2]);
+        double3 ghi = make_double3(h->global_hi[0], h->global_hi[1], h->global_hi[2]);
+        k_prepare<<<blocks, PREP_THREADS, 0, st>>>(v, h->block_partials, h->block_counter, h->d_domain, h->max_cells,
+                                                   h->have_global_domain, glo, ghi);
+        launches++;
+    }
+    k_cell_keys<<<blocks_for(n, 256), 256, 0, st>>>(v, h->d_domain, h->keys_in, h->idx_in);
+    launches++;
+    /* library plumbing (not counted in kernel_launches) */
+    CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, h->cub_tmp_bytes, h->keys_in, s.keys, h->idx_in, s.perm, n, 0, h->sort_bits, st));
+    k_cell_start<<<blocks_for(n + 1, 256), 256, 0, st>>>(s.keys, n, h->d_domain, s.cell_start);
+    k_gather<<<blocks_for(n, 256), 256, 0, st>>>(v, s);
+    launches += 2;
+    CU(cudaEventRecord(h->ev[1], st));
+
+    k_neighbours<<<blocks_for(n_targets, T), T, 0, st>>>(s, h->d_domain, n_targets, h->d_flags);
+    launches++;
+    CU(cudaEventRecord(h->ev[2], st));
+
+    /* kernel-sum density: always without INTEGRATE_DENSITY, else only for materials that ask for it */
+    const int use_rho_sorted = h->kernel_sum_density;
+    double *rho_sorted = h->rho_sorted;
+    if (use_rho_sorted) {
+        k_density<<<blocks_for(n_targets, T), T, 0, st>>>(s, v, rho_sorted, n_targets);
+        launches++;
+    }
+    CU(cudaEventRecord(h->ev[3], st));
+
+    k_pointwise<<<blocks_for(n, T), T, 0, st>>>(s, v, rho_sorted, use_rho_sorted);
+    launches++;
+    CU(cudaEventRecord(h->ev[4], st));
+#if TENSORIAL_CORRECTION
+    k_correction<<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets);
+    launches++;
+#endif
+    CU(cudaEventRecord(h->ev[5], st));
+    k_forces<<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets);
+    launches++;
+    CU(cudaEventRecord(h->ev[6], st));
+
+    h->stats.gravity_recomputed = 0;
+    if (v.selfgravity) {
+        int rc = gravity_eval(h, v, &launches);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(h->ev[7], st));
+
+    int flags[4];
+    CU(cudaMemcpyAsync(flags, h->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&h->h_domain, h->d_domain, sizeof(Domain), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+
+    b200sph_stats &S = h->stats;
+    S.kernel_launches = launches;
+    S.n_cells = h->h_domain.n_cells;
+    S.cell_size = h->h_domain.cell;
+    S.max_noi = flags[1];
+    cudaEventElapsedTime(&S.ms_total, h->ev[0], h->ev[7]);
+    cudaEventElapsedTime(&S.ms_sort, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&S.ms_neighbours, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&S.ms_density, h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&S.ms_pointwise, h->ev[3], h->ev[4]);
+    cudaEventElapsedTime(&S.ms_correction, h->ev[4], h->ev[5]);
+    cudaEventElapsedTime(&S.ms_forces, h->ev[5], h->ev[6]);
+    cudaEventElapsedTime(&S.ms_gravity, h->ev[6], h->ev[7]);
+    S.ms_scatter = 0.0f;
+
+    if (flags[0] != 0x7fffffff) {
+        if (offender) *offender = flags[0];
+        snprintf(h->err, sizeof(h->err), "particle %d has >= MAX_NUM_INTERACTIONS = %d interaction partners (reference: assert in src/tree.cu:917)",
+                 flags[0], MAX_NUM_INTERACTIONS);
+        return B200SPH_ERR_TOO_MANY_INTERACTIONS;
+    }
+    if (offender) *offender = -1;
+    return B200SPH_OK;
+}
+
+extern "C" int b200sph_export_interactions(b200sph_handle *h, int *interactions, int max_per_row)
+{
+    if (!h || !interactions || max_per_row <= 0 || h->s.n <= 0) return B200SPH_ERR_BAD_ARGUMENT;
+    CU(cudaSetDevice(h->device));
+    k_export_interactions<<<blocks_for(h->s.n, 128), 128, 0, h->stream>>>(h->s, interactions, max_per_row);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return B200SPH_OK;
+}
+
+extern "C" int b200sph_pressure(b200sph_handle *h, const b200sph_view *view)
+{
+    if (!h || !view || !h->materials_set) return B200SPH_ERR_BAD_ARGUMENT;
+    CU(cudaSetDevice(h->device));
+    k_pressure_only<<<blocks_for(view->n, 256), 256, 0, h->stream>>>(*view);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return B200SPH_OK;
+}
+
+extern "C" int b200sph_init_soundspeed(b200sph_handle *h, const b200sph_view *view)
+{
+    if (!h || !view || !h->materials_set) return B200SPH_ERR_BAD_ARGUMENT;
+    CU(cudaSetDevice(h->device));
+    k_init_soundspeed<<<blocks_for(view->n, 256), 256, 0, h->stream>>>(*view);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return B200SPH_OK;
+}
+
+extern "C" int b200sph_damage_limit(b200sph_handle *h, const b200sph_view *view)
+{
+    if (!h || !view || !h->materials_set) return B200SPH_ERR_BAD_ARGUMENT;
+#if FRAGMENTATION
+    CU(cudaSetDevice(h->device));
+    k_damage_limit<<<blocks_for(view->n, 256), 256, 0, h->stream>>>(*view);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+#endif
+    return B200SPH_OK;
+}
+
+/* upload of the material tables into constant memory (used by capi.cu) */
+int upload_materials(b200sph_handle *h, const MatParams *host, int n, const AneosTables &tables)
+{
+    CU(cudaMemcpyToSymbol(c_mat, host, sizeof(MatParams) * n));
+    CU(cudaMemcpyToSymbol(c_aneos, &tables, sizeof(AneosTables)));
+    return 0;
+}
+
+int sort_temp_bytes(int n_max, int bits, size_t *bytes)
+{
+    int *k = nullptr;
+    return cub::DeviceRadixSort::SortPairs(nullptr, *bytes, k, k, k, k, n_max, 0, bits) == cudaSuccess ? 0 : -1;
+}

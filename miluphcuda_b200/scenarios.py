@@ -448,8 +448,67 @@ def giant(n_target: int = 59899, solid: bool = False, seed: int = 7) -> Scenario
     )
 
 
-def make(config: str, n: int | None = None) -> Scenario:
+def stir(sc: Scenario, seed: int = 1234) -> Scenario:
+    """Perturb a pristine initial condition so that every term of the RHS is exercised.
+
+    Step-0 states of the shipped scenarios are at rest / stress-free, which makes most
+    rates vanish.  This applies seeded, bounded perturbations to positions (a fraction of
+    the local spacing), velocities, density, energy, deviatoric stress (non-symmetric on
+    purpose), damage and distension, staying inside each EOS's valid range.
+    """
+    rng = np.random.default_rng(seed)
+    n, dim = sc.n, sc.dim
+    u = lambda *shape: rng.uniform(-1.0, 1.0, size=shape)
+    sw = sc.switches()
+    if sc.h is not None:
+        spacing = sc.h / 2.1
+    else:
+        m = re.search(r"sml\s*=\s*([0-9.eE+-]+)", sc.material_cfg)
+        sml = float(m.group(1))
+        ratio = {"shocktube": 20.0, "sedov": 0.029 / 0.013, "rings": 0.25 / 0.075}.get(sc.config, 2.1)
+        spacing = np.full(n, sml / ratio)
+    if sc.config == "shocktube":
+        sc.x = np.sort(sc.x + 0.2 * spacing[:, None] * u(n, dim), axis=0)
+    else:
+        sc.x = sc.x + 0.15 * spacing[:, None] * u(n, dim)
+    cfgname = sc.config
+    if cfgname in ("shocktube", "sedov"):
+        sc.v = sc.v + 0.3 * u(n, dim)
+        sc.e = sc.e * (1.0 + 0.2 * u(n)) + (0.05 if cfgname == "sedov" else 0.0)
+        sc.m = sc.m * (1.0 + 0.05 * u(n))
+    elif cfgname == "rings":
+        sc.v = sc.v + 0.02 * u(n, dim)
+        sc.rho = sc.rho * (1.0 + 0.05 * u(n))
+        sc.S = 0.05 * u(n, dim * dim)
+    elif cfgname == "impact":
+        sc.v = sc.v + 60.0 * u(n, dim)
+        sc.rho = sc.rho * (1.0 + 0.04 * u(n))
+        sc.e = 2.0e4 * (1.0 + u(n)) + 1.0e3
+        hot = rng.random(n) < 0.03          # a few particles in the intermediate / vapour regimes
+        sc.e[hot] = rng.uniform(4.0e6, 3.0e7, size=int(hot.sum()))
+        sc.S = 2.0e7 * u(n, dim * dim)
+        sc.d = np.clip(0.45 * rng.random(n) - 0.05, 0.0, 1.0)
+        sc.alpha = 1.0 + 0.25 * rng.random(n)
+        sc.alpha[rng.random(n) < 0.05] = 1.0
+        sc.alpha[rng.random(n) < 0.01] = 0.995
+        sc.h = sc.h * (1.0 + 0.1 * u(n))
+    else:  # giant_hydro / giant_solid
+        sc.v = sc.v + 150.0 * u(n, dim)
+        sc.rho = sc.rho * (1.0 + 0.03 * u(n))
+        sc.e = sc.e * (1.0 + 0.3 * u(n))
+        hot = rng.random(n) < 0.03
+        sc.e[hot] = rng.uniform(2.5e6, 3.0e7, size=int(hot.sum()))
+        sc.rho[hot] *= rng.uniform(0.5, 1.0, size=int(hot.sum()))
+        if sw.get("SOLID", 0):
+            sc.S = 1.0e8 * u(n, dim * dim)
+            sc.d = np.clip(0.45 * rng.random(n) - 0.05, 0.0, 1.0)
+    return sc
+
+
+def make(config: str, n: int | None = None, stirred: bool = False) -> Scenario:
     """Scenario by config name at roughly n particles (None = the shipped resolution)."""
+    if stirred:
+        return stir(make(config, n))
     if config == "shocktube":
         return shocktube() if n is None else shocktube(dx=5e-4 * 3376.0 / n)
     if config == "sedov":

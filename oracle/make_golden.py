@@ -75,8 +75,8 @@ def run_reference(sc: scenarios.Scenario, workdir: str, env_extra: dict, log_nam
     return log
 
 
-def make_golden(config: str, n, out_dir: str) -> str:
-    sc = scenarios.make(config, n)
+def make_golden(config: str, n, out_dir: str, stirred: bool = False) -> str:
+    sc = scenarios.make(config, n, stirred=stirred)
     with tempfile.TemporaryDirectory() as wd:
         run_reference(sc, wd, {"REF_DUMP": os.path.join(wd, "dump"), "REF_DUMP_LISTS": "1"})
         d_in = read_dump(os.path.join(wd, "dump.in.bin"))
@@ -98,14 +98,17 @@ def make_golden(config: str, n, out_dir: str) -> str:
     for k, v in d1.items():
         payload["out1_" + k] = v
     for k, v in d2.items():
-        if k == "flaws":
-            continue
+        if k in d1 and np.array_equal(v, d1[k]):
+            continue  # unchanged by the second call
         payload["out2_" + k] = v
+    for k in list(d1):
+        if k in d_in and np.array_equal(d1[k], d_in[k]) and k != "noi":
+            payload.pop("out1_" + k)  # input passed through untouched
     payload["material_cfg"] = np.array(sc.material_cfg)
     for name, text in sc.includes.items():
         payload["include_" + name] = np.array(text)
     os.makedirs(out_dir, exist_ok=True)
-    path = os.path.join(out_dir, f"{config}.npz")
+    path = os.path.join(out_dir, f"{config}_stirred.npz" if stirred else f"{config}.npz")
     np.savez_compressed(path, **payload)
     return path
 
@@ -136,6 +139,7 @@ def main() -> None:
     ap.add_argument("--out", default=os.path.join(REPO, "gpurun_out", "golden"))
     ap.add_argument("--configs", default=",".join(GOLDEN_N))
     ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--n-stirred", type=int, default=1500)
     ap.add_argument("--time", default=None, help="config:n[,config:n...] -> time the reference RHS")
     ap.add_argument("--calls", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -151,8 +155,13 @@ def main() -> None:
     for cfg in args.configs.split(","):
         n = args.n if args.n is not None else GOLDEN_N[cfg]
         t0 = time.time()
-        path = make_golden(cfg, n, args.out)
-        print(f"golden {cfg}: {path} ({os.path.getsize(path) / 1e6:.2f} MB, {time.time() - t0:.1f}s)", flush=True)
+        for stirred in (False, True):
+            if stirred and n is not None:
+                n_use = args.n_stirred
+            else:
+                n_use = n
+            path = make_golden(cfg, n_use, args.out, stirred=stirred)
+            print(f"golden {cfg}: {path} ({os.path.getsize(path) / 1e6:.2f} MB, {time.time() - t0:.1f}s)", flush=True)
 
 
 if __name__ == "__main__":

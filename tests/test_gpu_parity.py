@@ -1,0 +1,143 @@
+"""GPU: the CUDA path (libb200sph_<config>.so through the C-ABI) against
+(1) golden vectors produced by the reference's own CUDA build and
+(2) the pinned oracle on larger seeded inputs.
+Bit-exact neighbour sets; 1e-9 relative (per-field scale) on every state and rate field."""
+import numpy as np
+import pytest
+
+import common
+from miluphcuda_b200 import api, scenarios
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def to_device(arrays):
+    return {k: torch.from_numpy(v).cuda() for k, v in arrays.items()}
+
+
+def to_host(dev):
+    return {k: v.cpu().numpy() for k, v in dev.items()}
+
+
+def run_cuda(config, arrays, cfg_path, meta, calls=1):
+    """Run `calls` x b200sph_rhs_eval on device copies of `arrays`; returns (host arrays per call, neighbour lists, stats)."""
+    n = meta["n"]
+    eng = api.RhsEngine(config, n_max=n, material_cfg=cfg_path)
+    dev = to_device(arrays)
+    view = api.make_view(dev, None, n, max_num_flaws=meta["max_num_flaws"], selfgravity=meta["selfgravity"],
+                         theta=meta["theta"], grav_const=eng.materials.grav_const)
+    outs = []
+    nbrs = None
+    for c in range(calls):
+        eng.rhs_eval(view)
+        torch.cuda.synchronize()
+        outs.append(to_host(dev))
+        if c == 0:
+            maxni = eng.lib.b200sph_switch_value(b"MAX_NUM_INTERACTIONS")
+            buf = torch.empty((n, maxni), dtype=torch.int32, device="cuda")
+            eng.export_interactions(buf, maxni)
+            nbrs = buf.cpu().numpy()
+    stats = eng.stats()
+    eng.close()
+    return outs, nbrs, stats
+
+
+def assert_neighbour_sets(nbrs, noi, ref_sets):
+    for i, ref in enumerate(ref_sets):
+        got = np.sort(nbrs[i, : noi[i]])
+        assert np.array_equal(got, ref), f"neighbour set of particle {i} differs: {got} vs {ref}"
+        assert (nbrs[i, noi[i]:] == -1).all()
+
+
+@pytest.mark.parametrize("case", common.GOLDEN_CASES)
+def test_cuda_matches_reference_golden(case):
+    config = common.config_of(case)
+    g = common.load_golden(case)
+    arrays, meta = common.state_from_golden(g, config)
+    td, cfg = common.tmp_material(g)
+    try:
+        outs, nbrs, stats = run_cuda(config, arrays, cfg, meta, calls=2)
+    finally:
+        td.cleanup()
+    assert stats["kernel_launches"] > 0
+    assert np.array_equal(outs[0]["noi"], g["out1_noi"])
+    assert_neighbour_sets(nbrs, outs[0]["noi"], common.golden_neighbours(g))
+    for stage, out in zip(("out1", "out2"), outs):
+        rep = common.compare_fields(out, g, stage, common.RATE_FIELDS + common.STATE_FIELDS)
+        bad = {k: v for k, v in rep.items() if not v <= common.RTOL}
+        assert not bad, f"{stage}: relative errors above {common.RTOL}: {bad}"
+        for name in common.INT_COMPARE:
+            ref = common.golden_expected(g, stage, name)
+            if name in out and ref is not None:
+                assert np.array_equal(out[name], ref), f"{stage}: {name}"
+
+
+ORACLE_SIZES = {"shocktube": 20000, "sedov": 40000, "rings": 40000, "impact": 30000, "giant_hydro": 30000, "giant_solid": 30000}
+
+
+def scenario_arrays(sc):
+    """Caller-order arrays for a generated scenario, as the reference's reader + init would set them."""
+    sw = sc.switches()
+    n, dim = sc.n, sc.dim
+    max_flaws = sw.get("MAX_NUM_FLAWS", 1)
+    p_fields, rhs_fields = api.fields_for(sw, sc.selfgravity)
+    arrays = {}
+    for name in p_fields + rhs_fields:
+        dtype = np.int32 if name in api.INT_FIELDS else np.float64
+        arrays[name] = np.zeros(api.field_shape(name, n, dim, max_flaws), dtype=dtype)
+    for k, ax in enumerate("xyz"[:dim]):
+        arrays[ax][:] = sc.x[:, k]
+        arrays["v" + ax][:] = sc.v[:, k]
+    arrays["m"][:] = sc.m
+    arrays["materialId"][:] = sc.mat
+    if sc.rho is not None:
+        arrays["rho"][:] = sc.rho
+    if sc.e is not None:
+        arrays["e"][:] = sc.e
+    if sc.S is not None:
+        arrays["S"][:] = sc.S.reshape(-1)
+    if sc.d is not None:
+        arrays["d"][:] = sc.d
+        arrays["numFlaws"][:] = sc.num_flaws
+        arrays["flaws"][:] = sc.flaws.reshape(-1)
+        arrays["numActiveFlaws"][:] = np.minimum(np.ceil(sc.num_flaws * sc.d ** dim), sc.num_flaws).astype(np.int32)
+    if sc.alpha is not None:
+        arrays["alpha_jutzi"][:] = sc.alpha
+        arrays["pold"][:] = sc.pold
+    return arrays, dict(n=n, max_num_flaws=max_flaws, selfgravity=sc.selfgravity, theta=sc.theta)
+
+
+@pytest.mark.parametrize("config", common.CONFIGS)
+def test_cuda_matches_oracle_larger(config, tmp_path):
+    sc = scenarios.make(config, ORACLE_SIZES[config], stirred=True)
+    arrays, meta = scenario_arrays(sc)
+    _, cfg = sc.write_inputs(str(tmp_path), basename="unused.0000") if False else (None, None)
+    cfg = str(tmp_path / "material.cfg")
+    with open(cfg, "w") as fh:
+        fh.write(sc.material_cfg)
+    for name, text in sc.includes.items():
+        (tmp_path / name).write_text(text)
+    mats = api.MaterialTables(config, cfg)
+    if sc.h is not None:
+        arrays["h"][:] = sc.h
+    else:
+        arrays["h"][:] = mats.table("matSml")[arrays["materialId"]]
+    arrays["h0"][:] = arrays["h"]
+    ref = {k: v.copy() for k, v in arrays.items()}
+    outs, nbrs, stats = run_cuda(config, arrays, cfg, meta, calls=2)
+    for call in range(2):
+        rc, off, inter = common.oracle_rhs(config, ref, mats, meta)
+        assert rc == 0
+        out = outs[call]
+        assert np.array_equal(out["noi"], ref["noi"])
+        if call == 0:
+            sets = [inter[i, : ref["noi"][i]] for i in range(meta["n"])]
+            assert_neighbour_sets(nbrs, out["noi"], sets)
+        bad = {}
+        for name in common.RATE_FIELDS + common.STATE_FIELDS:
+            if name in out:
+                err = common.field_error(out[name], ref[name])
+                if not err <= common.RTOL:
+                    bad[name] = err
+        assert not bad, f"call {call + 1}: relative errors above {common.RTOL}: {bad}"
