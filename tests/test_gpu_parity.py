@@ -126,6 +126,7 @@ def test_cuda_matches_oracle_larger(config, tmp_path):
     arrays["h0"][:] = arrays["h"]
     ref = {k: v.copy() for k, v in arrays.items()}
     outs, nbrs, stats = run_cuda(config, arrays, cfg, meta, calls=2)
+    first_scale = {}
     for call in range(2):
         rc, off, inter = common.oracle_rhs(config, ref, mats, meta)
         assert rc == 0
@@ -137,7 +138,11 @@ def test_cuda_matches_oracle_larger(config, tmp_path):
         bad = {}
         for name in common.RATE_FIELDS + common.STATE_FIELDS:
             if name in out:
-                err = common.field_error(out[name], ref[name])
+                # second call: fields that are pure rounding noise there (edotp once S sits on the
+                # yield surface) are judged against their first-call magnitude
+                err = common.field_error(out[name], ref[name], first_scale.get(name, 0.0))
+                if call == 0:
+                    first_scale[name] = float(np.sqrt(np.mean(ref[name].astype(np.float64) ** 2)))
                 if not err <= common.RTOL:
                     bad[name] = err
         assert not bad, f"call {call + 1}: relative errors above {common.RTOL}: {bad}"
