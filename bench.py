@@ -1,0 +1,335 @@
+#!/usr/bin/env python3
+"""bench.py -- particle-updates/s of the SPH right-hand side on N B200s.
+
+One "step" = one evaluation of the hot path (what miluphcuda's rightHandSide() does,
+reference src/rhs.cu:143-861) over every particle of a synthetic scenario; the metric
+is RHS evaluations x particles / second (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sedov] [--particles 1000000]
+  python bench.py --impl reference ...      # the reference's own implementation, same metric/config
+
+Arms
+  default   : libb200sph_<workload>.so through the C-ABI.  `value` = inputs resident in HBM,
+              per-step CUDA events on the launching stream, L2 flushed between steps (untimed);
+              `e2e` = the same call with HOST (pinned) buffers, copies inside the timed region.
+  reference : miluphcuda has no CPU path (north_star), so the reference arm runs the reference's
+              own CUDA build (oracle/_ref/miluphcuda_<workload>, compiled unmodified from
+              /root/reference for sm_100a) on the same GPU, one rightHandSide() per step.
+              If that binary is missing, the CPU oracle port is timed instead (kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "sph_particle_updates_per_s"
+UNIT = "particle-updates/s"
+DEFAULT_PARTICLES = {"shocktube": 10000, "sedov": 1000000, "rings": 1000000, "impact": 1000000,
+                     "giant_hydro": 1000000, "giant_solid": 1000000}
+
+
+# ----------------------------------------------------------------------------- roofline constants
+def load_constants() -> dict:
+    with open(os.path.join(REPO, "miluphcuda_b200", "roofline_constants.json")) as fh:
+        return json.load(fh)
+
+
+def measured_peaks() -> dict:
+    peaks = {"hbm_gbs": 6650.0, "hbm_source": "fallback (B200_PROFILING.md)", "fp64_tflops": 34.1,
+             "fp64_source": "measured, tools/fp64_peak.cu on this pool (profiles/r01_fp64_peak.json)"}
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            mp = json.load(fh)
+        if "hbm_gbs" in mp:
+            peaks["hbm_gbs"] = float(mp["hbm_gbs"])
+            peaks["hbm_source"] = "measured (MEASURED_PEAKS.json)"
+    fp = os.path.join(REPO, "profiles", "r01_fp64_peak.json")
+    if os.path.exists(fp):
+        with open(fp) as fh:
+            peaks["fp64_tflops"] = float(json.load(fh)["fp64_tflops_sustained"])
+    return peaks
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference_arm(args, rank: int, world: int) -> None:
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    workload, n = args.workload, args.particles
+    binary = os.path.join(REPO, "oracle", "_ref", f"miluphcuda_{workload}")
+    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{workload} (synthetic, {n} particles requested)", "particles": n}}
+    if os.path.exists(binary):
+        import make_golden
+        res = make_golden.time_reference(workload, n, calls=args.steps, warmup=args.warmup)
+        value = res["updates_per_s"]
+        base["config"]["particles"] = res["n"]
+        base["config"]["workload"] = f"{workload} (synthetic, {res['n']} particles)"
+        base.update({"value": value, "ms_per_step": res["ms_per_call"],
+                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+                                      "sample": ("miluphcuda has no CPU path: the UNMODIFIED reference CUDA build (sm_100a, quiet debug flags) "
+                                                 f"ran {args.steps} rightHandSide() calls on ONE B200 after {args.warmup} warm-up calls; 1 host thread; "
+                                                 "a single GPU regardless of --gpus (the reference is single-GPU)")},
+                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "reference_kernel_ms": res["kernel_ms_last"]})
+    else:
+        value, cores, sample, ms = time_oracle_port(workload, min(n, 200000), budget_s=20.0)
+        base.update({"value": value, "ms_per_step": ms,
+                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base), flush=True)
+
+
+def time_oracle_port(workload: str, n: int, budget_s: float = 15.0):
+    """CPU restatement (oracle/sph_oracle.c, OpenMP) on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import common  # tests/common.py: oracle binding
+    from miluphcuda_b200 import api, scenarios, state
+    sc = scenarios.make(workload, n)
+    with tempfile.TemporaryDirectory() as td:
+        cfg = state.write_material_files(sc, td)
+        mats = api.MaterialTables(workload, cfg)
+        arrays, meta = state.scenario_arrays(sc, mats)
+        cores = os.cpu_count() or 1
+        common.oracle_rhs(workload, arrays, mats, meta)  # warm-up (page faults, omp pool)
+        calls, t0 = 0, time.time()
+        while True:
+            rc, off, _ = common.oracle_rhs(workload, arrays, mats, meta)
+            if rc != 0:
+                raise RuntimeError(f"oracle rc={rc}")
+            calls += 1
+            if time.time() - t0 > budget_s or calls >= 20:
+                break
+        dt = time.time() - t0
+    value = sc.n * calls / dt
+    sample = f"oracle/sph_oracle.c (OpenMP, {cores} threads) on {workload} with {sc.n} particles, {calls} RHS calls in {dt:.1f} s"
+    return value, cores, sample, dt / calls * 1e3
+
+
+# ----------------------------------------------------------------------------- our arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sedov", choices=list(DEFAULT_PARTICLES))
+    ap.add_argument("--particles", type=int, default=None, help="particles per GPU (weak scaling)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.particles is None:
+        args.particles = DEFAULT_PARTICLES[args.workload]
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from miluphcuda_b200 import api, scenarios, state
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the SPH right-hand side has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    workload = args.workload
+    sc = scenarios.make(workload, args.particles)
+    tmp = tempfile.TemporaryDirectory()
+    cfg = state.write_material_files(sc, tmp.name)
+    eng = api.RhsEngine(workload, n_max=sc.n, device=local_rank, material_cfg=cfg)
+    arrays, meta = state.scenario_arrays(sc, eng.materials)
+    n = sc.n
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    dev = {k: torch.from_numpy(v).cuda() for k, v in arrays.items()}
+    view = api.make_view(dev, None, n, max_num_flaws=meta["max_num_flaws"], selfgravity=meta["selfgravity"],
+                         theta=meta["theta"], grav_const=eng.materials.grav_const)
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 512 MiB > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.rhs_eval(view)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_ms = {}
+    launches = 0
+    t_wall0 = time.time()
+    for k in range(args.steps):
+        flush.fill_(float(k))           # evict L2 between timed steps (not timed)
+        ev[k][0].record(stream)
+        eng.rhs_eval(view)
+        ev[k][1].record(stream)
+        st = eng.stats()
+        launches += st["kernel_launches"]
+        for key, val in st.items():
+            if key.startswith("ms_"):
+                stage_ms[key] = stage_ms.get(key, 0.0) + val
+    barrier()
+    t_wall = time.time() - t_wall0
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    stats = eng.stats()
+
+    # max over ranks of the device time for exactly K steps
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(n)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    total_particles = float(cnt.item())
+    value = total_particles * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end: host (pinned) buffers through the C-ABI, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        pinned = {k: torch.from_numpy(v).pin_memory() for k, v in arrays.items()}
+        hview = api.make_view(pinned, None, n, max_num_flaws=meta["max_num_flaws"], selfgravity=meta["selfgravity"],
+                              theta=meta["theta"], grav_const=eng.materials.grav_const)
+        h2d = d2h = 0
+        for _ in range(2):
+            h2d, d2h = eng.rhs_eval_host(hview)
+        barrier()
+        e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            h2d, d2h = eng.rhs_eval_host(hview)
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_particles * e_steps / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
+               "timing": "host wall clock around b200sph_rhs_eval_host (sync on both sides), max over ranks"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the pair-force loop), timed live by CUDA events on its stream
+    const = load_constants()
+    peaks = measured_peaks()
+    kind = const["workloads"][workload]
+    total_noi = float(dev["noi"].sum().item())
+    pairs = total_noi
+    ms_forces = stage_ms.get("ms_forces", 0.0) / args.steps
+    flops = kind["force_flop_per_pair"] * pairs + kind["force_flop_per_particle"] * n
+    bytes_alg = kind["force_bytes_per_particle"] * n
+    tf = flops / (ms_forces * 1e-3) / 1e12 if ms_forces > 0 else 0.0
+    gbs = bytes_alg / (ms_forces * 1e-3) / 1e9 if ms_forces > 0 else 0.0
+    roof = {"bound": "fp64", "kernel": "k_forces", "achieved": tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
+            "frac": tf / peaks["fp64_tflops"], "traffic": None, "peak_source": peaks["fp64_source"],
+            "ms_per_launch": ms_forces, "pairs_per_launch": pairs, "flop_per_pair": kind["force_flop_per_pair"],
+            "hbm": {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                    "peak_source": peaks["hbm_source"], "bytes_per_particle": kind["force_bytes_per_particle"]},
+            "share_of_step": ms_forces * args.steps / total_ms if total_ms > 0 else None,
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v_cpu, cores, sample, _ = time_oracle_port(workload, min(n, 250000), budget_s=12.0)
+        cpu = {"value": v_cpu, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{workload} (synthetic, {n} particles per GPU)", "particles": int(total_particles),
+                   "mean_interactions": total_noi / n, "l2": "512 MiB buffer written between timed steps (untimed)",
+                   "timing": "per-step CUDA events on the launching stream, summed over K steps, max over ranks",
+                   "multi_gpu": "replicas" if world > 1 else "single"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
+        "search_grid": {"cells": stats["n_cells"], "cell_size": stats["cell_size"], "max_interactions": stats["max_noi"]},
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

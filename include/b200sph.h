@@ -188,6 +188,10 @@ int b200sph_export_interactions(b200sph_handle *h, int *interactions, int max_pe
 
 int b200sph_get_stats(const b200sph_handle *h, b200sph_stats *out);
 
+/* Run on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = the legacy default
+ * stream the reference uses for everything) instead of the library's own stream. */
+int b200sph_set_stream(b200sph_handle *h, void *cuda_stream);
+
 /* Multi-GPU.  Each rank owns a contiguous slab of the global search grid; halo
  * particles received from neighbouring ranks are appended after the owned ones ([n_owned, n)).
  * rhs_eval computes all rates for owned particles only; pointwise quantities are recomputed on

@@ -118,6 +118,7 @@ _EXPORTS = {
     "b200sph_init_soundspeed": (C.c_int, [C.c_void_p, C.POINTER(View)]),
     "b200sph_export_interactions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "b200sph_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "b200sph_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200sph_set_owned": (C.c_int, [C.c_void_p, C.c_int]),
     "b200sph_set_global_domain": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
@@ -305,6 +306,9 @@ class RhsEngine:
         st = Stats()
         self._check(self.lib.b200sph_get_stats(self.handle, C.byref(st)))
         return st.as_dict()
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        self._check(self.lib.b200sph_set_stream(self.handle, cuda_stream))
 
     def set_owned(self, n_owned: int) -> None:
         self._check(self.lib.b200sph_set_owned(self.handle, n_owned))

@@ -121,6 +121,7 @@ extern "C" int b200sph_create(b200sph_handle **out, int n_max, int device, uint6
 #undef ALLOC
     e = cudaMemset(h->block_counter, 0, 4 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    h->own_stream = (e == cudaSuccess);
     for (int k = 0; k < 12 && e == cudaSuccess; k++) e = cudaEventCreate(&h->ev[k]);
     if (e != cudaSuccess) {
         snprintf(g_create_error, sizeof(g_create_error), "stream/event setup: %s", cudaGetErrorString(e));
@@ -152,7 +153,7 @@ extern "C" int b200sph_destroy(b200sph_handle *h)
     cudaFree(h->aneos_buf);
     for (int k = 0; k < 12; k++)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     free(h);
     return B200SPH_OK;
 }
@@ -271,6 +272,15 @@ extern "C" int b200sph_get_stats(const b200sph_handle *h, b200sph_stats *out)
 {
     if (!h || !out) return B200SPH_ERR_BAD_ARGUMENT;
     *out = h->stats;
+    return B200SPH_OK;
+}
+
+extern "C" int b200sph_set_stream(b200sph_handle *h, void *cuda_stream)
+{
+    if (!h) return B200SPH_ERR_BAD_ARGUMENT;
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->own_stream = 0;
+    h->stream = (cudaStream_t)cuda_stream;
     return B200SPH_OK;
 }
 

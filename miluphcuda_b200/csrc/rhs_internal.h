@@ -55,6 +55,7 @@ struct Sorted {
 struct b200sph_handle {
     int n_max, device;
     cudaStream_t stream;
+    int own_stream;
     cudaEvent_t ev[12];
     Sorted s;
     Domain *d_domain;           /* device */

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import common
-from miluphcuda_b200 import api, scenarios
+from miluphcuda_b200 import api, scenarios, state
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -76,54 +76,12 @@ def test_cuda_matches_reference_golden(case):
 ORACLE_SIZES = {"shocktube": 20000, "sedov": 40000, "rings": 40000, "impact": 30000, "giant_hydro": 30000, "giant_solid": 30000}
 
 
-def scenario_arrays(sc):
-    """Caller-order arrays for a generated scenario, as the reference's reader + init would set them."""
-    sw = sc.switches()
-    n, dim = sc.n, sc.dim
-    max_flaws = sw.get("MAX_NUM_FLAWS", 1)
-    p_fields, rhs_fields = api.fields_for(sw, sc.selfgravity)
-    arrays = {}
-    for name in p_fields + rhs_fields:
-        dtype = np.int32 if name in api.INT_FIELDS else np.float64
-        arrays[name] = np.zeros(api.field_shape(name, n, dim, max_flaws), dtype=dtype)
-    for k, ax in enumerate("xyz"[:dim]):
-        arrays[ax][:] = sc.x[:, k]
-        arrays["v" + ax][:] = sc.v[:, k]
-    arrays["m"][:] = sc.m
-    arrays["materialId"][:] = sc.mat
-    if sc.rho is not None:
-        arrays["rho"][:] = sc.rho
-    if sc.e is not None:
-        arrays["e"][:] = sc.e
-    if sc.S is not None:
-        arrays["S"][:] = sc.S.reshape(-1)
-    if sc.d is not None:
-        arrays["d"][:] = sc.d
-        arrays["numFlaws"][:] = sc.num_flaws
-        arrays["flaws"][:] = sc.flaws.reshape(-1)
-        arrays["numActiveFlaws"][:] = np.minimum(np.ceil(sc.num_flaws * sc.d ** dim), sc.num_flaws).astype(np.int32)
-    if sc.alpha is not None:
-        arrays["alpha_jutzi"][:] = sc.alpha
-        arrays["pold"][:] = sc.pold
-    return arrays, dict(n=n, max_num_flaws=max_flaws, selfgravity=sc.selfgravity, theta=sc.theta)
-
-
 @pytest.mark.parametrize("config", common.CONFIGS)
 def test_cuda_matches_oracle_larger(config, tmp_path):
     sc = scenarios.make(config, ORACLE_SIZES[config], stirred=True)
-    arrays, meta = scenario_arrays(sc)
-    _, cfg = sc.write_inputs(str(tmp_path), basename="unused.0000") if False else (None, None)
-    cfg = str(tmp_path / "material.cfg")
-    with open(cfg, "w") as fh:
-        fh.write(sc.material_cfg)
-    for name, text in sc.includes.items():
-        (tmp_path / name).write_text(text)
+    cfg = state.write_material_files(sc, str(tmp_path))
     mats = api.MaterialTables(config, cfg)
-    if sc.h is not None:
-        arrays["h"][:] = sc.h
-    else:
-        arrays["h"][:] = mats.table("matSml")[arrays["materialId"]]
-    arrays["h0"][:] = arrays["h"]
+    arrays, meta = state.scenario_arrays(sc, mats)
     ref = {k: v.copy() for k, v in arrays.items()}
     outs, nbrs, stats = run_cuda(config, arrays, cfg, meta, calls=2)
     first_scale = {}
