@@ -160,12 +160,14 @@
 #define B200SPH_CONFIG_NAME "custom"
 #endif
 
-/* EOS ids, reference: include/pressure.h:31-48 */
+/* EOS ids, reference: include/pressure.h:31-48 (skipped when compiled next to the reference's own headers) */
+#ifndef B200SPH_NO_EOS_ENUM
 enum {
     EOS_TYPE_ACCRETED = -2, EOS_TYPE_IGNORE = -1, EOS_TYPE_POLYTROPIC_GAS = 0, EOS_TYPE_MURNAGHAN = 1,
     EOS_TYPE_TILLOTSON = 2, EOS_TYPE_ISOTHERMAL_GAS = 3, EOS_TYPE_REGOLITH = 4, EOS_TYPE_JUTZI = 5,
     EOS_TYPE_JUTZI_MURNAGHAN = 6, EOS_TYPE_ANEOS = 7, EOS_TYPE_VISCOUS_REGOLITH = 8, EOS_TYPE_IDEAL_GAS = 9,
     EOS_TYPE_SIRONO = 10, EOS_TYPE_EPSILON = 11, EOS_TYPE_LOCALLY_ISOTHERMAL_GAS = 12, EOS_TYPE_JUTZI_ANEOS = 13
 };
+#endif
 
 #endif

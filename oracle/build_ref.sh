@@ -15,7 +15,11 @@
 #   * src/euler.cu is replaced by oracle/ref_hook.cu (dump + timing hook that
 #     calls the reference's own rightHandSide())
 #
-# usage: oracle/build_ref.sh [config ...]     (default: all six)
+# Drop-in variant: a config written as "<name>+b200" additionally replaces src/rhs.cu by
+# integration/rhs_b200.cu and links libb200sph_<name>.so, i.e. the reference host (main, I/O,
+# libconfig, integrators) running on the new kernels -> oracle/_ref/miluphcuda_<name>_b200.
+#
+# usage: oracle/build_ref.sh [config[+b200] ...]     (default: all six, reference only)
 set -euo pipefail
 
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -43,10 +47,13 @@ CONFIGS=("$@")
 if [ ${#CONFIGS[@]} -eq 0 ]; then CONFIGS=(shocktube sedov rings impact giant_hydro giant_solid); fi
 
 mkdir -p "$OUT"
-for cfg in "${CONFIGS[@]}"; do
+for spec in "${CONFIGS[@]}"; do
+  cfg="${spec%+b200}"
+  dropin=0; [ "$spec" != "$cfg" ] && dropin=1
+  suffix=""; [ $dropin -eq 1 ] && suffix="_b200"
   src_dir="${CFGDIR[$cfg]:-}"
   if [ -z "$src_dir" ]; then echo "unknown config $cfg" >&2; exit 2; fi
-  B="$OUT/build/$cfg"
+  B="$OUT/build/$cfg$suffix"
   rm -rf "$B"; mkdir -p "$B/include" "$B/obj"
   for h in "$REF"/include/*.h; do
     n="$(basename "$h")"
@@ -59,18 +66,25 @@ for cfg in "${CONFIGS[@]}"; do
   sed -E 's/^(#define[[:space:]]+DEBUG_(TIMESTEP|TREE|GRAVITY|RHS))[[:space:]]+1/\1 0/' \
       "$REF/include/miluph.h" > "$B/include/miluph.h"
 
-  NVFLAGS="$ARCH -x cu -c -dc -O3 -w -Xcompiler -O3,-pthread -DVERSION=\"ref-sm100a\" -I$B/include -I$REPO/miluphcuda_b200/csrc"
+  NVFLAGS="$ARCH -x cu -c -dc -O3 -w -Xcompiler -O3,-pthread -DVERSION=\"ref-sm100a\" -I$B/include -I$REPO/miluphcuda_b200/csrc -I$REPO/include"
   echo "[build_ref] $cfg: compiling"
   ( for f in "$REF"/src/*.cu; do
       n="$(basename "$f" .cu)"
       [ "$n" = "euler" ] && continue
+      [ $dropin -eq 1 ] && [ "$n" = "rhs" ] && continue
       echo "$f $B/obj/$n.o"
     done
     echo "$HERE/ref_hook.cu $B/obj/ref_hook.o"
+    [ $dropin -eq 1 ] && echo "$REPO/integration/rhs_b200.cu $B/obj/rhs_b200.o"
   ) | xargs -P "$(nproc)" -n 2 sh -c "$NVCC $NVFLAGS -o \"\$1\" \"\$0\""
   gcc -O2 -c "$REPO/miluphcuda_b200/csrc/libconfig_lite.c" -o "$B/obj/libconfig_lite.o"
-  $NVCC $ARCH "$B"/obj/*.o -lcudart -lpthread -o "$OUT/miluphcuda_$cfg"
+  LINK_EXTRA=""
+  if [ $dropin -eq 1 ]; then
+    python3 "$REPO/miluphcuda_b200/build.py" "$cfg" > /dev/null
+    LINK_EXTRA="-L$REPO/miluphcuda_b200/lib -lb200sph_$cfg -Xlinker -rpath -Xlinker \$ORIGIN/../../miluphcuda_b200/lib"
+  fi
+  $NVCC $ARCH "$B"/obj/*.o -lcudart -lpthread $LINK_EXTRA -o "$OUT/miluphcuda_$cfg$suffix"
   rm -rf "$B"
-  echo "[build_ref] $cfg: $OUT/miluphcuda_$cfg"
+  echo "[build_ref] $spec: $OUT/miluphcuda_$cfg$suffix"
 done
 rmdir "$OUT/build" 2>/dev/null || true
