@@ -71,11 +71,11 @@ for spec in "${CONFIGS[@]}"; do
   ( for f in "$REF"/src/*.cu; do
       n="$(basename "$f" .cu)"
       [ "$n" = "euler" ] && continue
-      [ $dropin -eq 1 ] && [ "$n" = "rhs" ] && continue
+      if [ $dropin -eq 1 ] && [ "$n" = "rhs" ]; then continue; fi
       echo "$f $B/obj/$n.o"
     done
     echo "$HERE/ref_hook.cu $B/obj/ref_hook.o"
-    [ $dropin -eq 1 ] && echo "$REPO/integration/rhs_b200.cu $B/obj/rhs_b200.o"
+    if [ $dropin -eq 1 ]; then echo "$REPO/integration/rhs_b200.cu $B/obj/rhs_b200.o"; fi
   ) | xargs -P "$(nproc)" -n 2 sh -c "$NVCC $NVFLAGS -o \"\$1\" \"\$0\""
   gcc -O2 -c "$REPO/miluphcuda_b200/csrc/libconfig_lite.c" -o "$B/obj/libconfig_lite.o"
   LINK_EXTRA=""
