@@ -95,15 +95,9 @@ extern "C" int b200sph_create(b200sph_handle **out, int n_max, int device, uint6
     } while (0)
     Sorted &s = h->s;
     ALLOC(s.perm, n); ALLOC(s.keys, n); ALLOC(s.cell_start, (size_t)h->max_cells + 2);
-    ALLOC(s.pos4, n); ALLOC(s.vel4, n); ALLOC(s.gas4, n); ALLOC(s.mat, n);
+    ALLOC(s.pos4, n); ALLOC(s.vel4, n); ALLOC(s.gas4, n); ALLOC(s.mat, n); ALLOC(s.srch, n);
 #if SOLID
-    ALLOC(s.sig, n * DD);
-#if TENSORIAL_CORRECTION
-    ALLOC(s.cmat, n * DD);
-#endif
-#if ARTIFICIAL_STRESS
-    ALLOC(s.rart, n * DD);
-#endif
+    ALLOC(s.ten, n * TEN_RECS);
 #endif
     ALLOC(s.nbr, tiles * NBR_TILE * (size_t)MAX_NUM_INTERACTIONS);
     ALLOC(s.noi, n);
@@ -146,7 +140,7 @@ extern "C" int b200sph_destroy(b200sph_handle *h)
     gravity_tree_destroy(h);
     Sorted &s = h->s;
     cudaFree(s.perm); cudaFree(s.keys); cudaFree(s.cell_start); cudaFree(s.pos4); cudaFree(s.vel4); cudaFree(s.gas4);
-    cudaFree(s.mat); cudaFree(s.sig); cudaFree(s.cmat); cudaFree(s.rart); cudaFree(s.nbr); cudaFree(s.noi);
+    cudaFree(s.mat); cudaFree(s.srch); cudaFree(s.ten); cudaFree(s.nbr); cudaFree(s.noi);
     cudaFree(h->keys_in); cudaFree(h->idx_in); cudaFree(h->rho_sorted); cudaFree(h->block_partials);
     cudaFree(h->block_counter); cudaFree(h->d_flags); cudaFree(h->d_domain); cudaFree(h->cub_tmp);
     cudaFree(h->stage);
@@ -222,8 +216,10 @@ extern "C" int b200sph_set_materials(b200sph_handle *h, const b200sph_materials 
 #undef GETI
 #undef GETD
     int kernel_sum = !INTEGRATE_DENSITY;
+    h->s.any_eos_ignore = 0;
     for (int k = 0; k < n; k++) {
         const int eos = host[k].eos;
+        if (eos == EOS_TYPE_IGNORE) h->s.any_eos_ignore = 1;
         if (host[k].density_via_kernel_sum > 0) kernel_sum = 1;
         if (!mat->mat_f_sml_min) host[k].f_sml_min = 1.0;
         if (!mat->mat_f_sml_max) host[k].f_sml_max = 1.0;

@@ -10,10 +10,11 @@
  *   keys[n], perm[n]            cell index of each particle / sorted -> caller index
  *   cell_start[n_cells + 1]     first sorted slot of every cell (x fastest), so the
  *                               particles of a row of x-adjacent cells are one range
- *   pos4[n]   = {x, y, z, h}    32-byte records, one LDG.128 pair per candidate
+ *   pos4[n]   = {x, y, z, h}    32-byte records, one LDG.256 per candidate
  *   vel4[n]   = {vx, vy, vz, m}
  *   gas4[n]   = {p/rho^2 (hydro) or 1/rho^2 (solid), c_s, rho, m/rho}
- *   sig[n*DD], cmat[n*DD], rart[n*DD]   sigma/rho^2, correction matrix, R/rho^2 (solid)
+ *   srch[n]   = {u_x, u_y, u_z, thr} FP32, 16 bytes: conservative pre-filter of the neighbour search
+ *   ten[n*TEN_RECS]             sigma/rho^2, correction matrix, R/rho^2 packed (solid)
  *   nbr[(tile*MAX_NUM_INTERACTIONS + k)*32 + lane], noi[n]
  *                               neighbour lists, interleaved per 32-particle tile so the
  *                               k-th entries of a warp's particles share one 128-byte line
@@ -29,6 +30,57 @@
 
 #define NBR_TILE 32
 
+/* ------------------------------------------------------------------ 32-byte records
+ * Every per-candidate quantity a pair loop gathers lives in 32-byte records that are fetched
+ * with ONE 256-bit load (sm_100a LDG.E.256): the pair loops are bound by L1TEX wavefronts
+ * (one per distinct 128-byte line per instruction, profiles/r01_ncu_full_sedov_v0_summary.csv),
+ * so halving the number of load instructions per pair halves their cost. */
+struct __align__(32) Rec4 {
+    double x, y, z, w;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ Rec4 ld_rec(const Rec4 *ptr)
+{
+    /* read-only for the lifetime of the reading kernel (written by an earlier launch) */
+    Rec4 r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(ptr));
+    return r;
+}
+__device__ __forceinline__ void st_rec(Rec4 *ptr, const Rec4 &v)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+#endif
+
+/* Solid tensors of a particle, packed into TEN_RECS records: sigma/rho^2, then the tensorial
+ * correction matrix, then R/rho^2 (artificial stress).  sigma is stored as its upper triangle
+ * when the switch set symmetrises S (symmetrizeStress runs under FRAGMENTATION or a plasticity
+ * model, reference src/rhs.cu:462-470) -- it is then bitwise symmetric -- and in full otherwise.
+ * C = pinv(symmetric) and R = V^T diag V are symmetric up to one rounding; the upper triangle is
+ * used for both halves (difference ~1e-16 relative, far inside the 1e-9 gate). */
+#if SOLID
+#define TEN_SIG_SYM (FRAGMENTATION || B200_PLASTICITY)
+#define TEN_NSYM (DIM * (DIM + 1) / 2)
+#define TEN_NSIG (TEN_SIG_SYM ? TEN_NSYM : DIM * DIM)
+#define TEN_SIG_OFF 0
+#define TEN_C_OFF (TEN_SIG_OFF + TEN_NSIG)
+#define TEN_R_OFF (TEN_C_OFF + (TENSORIAL_CORRECTION ? TEN_NSYM : 0))
+#define TEN_DOUBLES (TEN_R_OFF + (ARTIFICIAL_STRESS ? TEN_NSYM : 0))
+#define TEN_RECS ((TEN_DOUBLES + 3) / 4)
+#ifdef __CUDACC__
+__host__ __device__ constexpr int ten_sym(int a, int b)
+{
+    return (a <= b) ? (a * DIM - a * (a - 1) / 2 + (b - a)) : (b * DIM - b * (b - 1) / 2 + (a - b));
+}
+__host__ __device__ constexpr int ten_sig(int a, int b) { return TEN_SIG_OFF + (TEN_SIG_SYM ? ten_sym(a, b) : a * DIM + b); }
+__host__ __device__ constexpr int ten_c(int a, int b) { return TEN_C_OFF + ten_sym(a, b); }
+__host__ __device__ constexpr int ten_r(int a, int b) { return TEN_R_OFF + ten_sym(a, b); }
+#endif
+#else
+#define TEN_RECS 0
+#endif
+
 /* search grid and root cube, computed on the device each call */
 struct Domain {
     double lo[3], hi[3];        /* bounding box of all particles */
@@ -43,12 +95,14 @@ struct Domain {
 
 struct Sorted {
     int n;
+    int any_eos_ignore;         /* a material with eos.type IGNORE exists: pair loops must look at mat[j] */
     int *perm;                  /* sorted slot -> caller index */
     int *keys;
     int *cell_start;
-    double4 *pos4, *vel4, *gas4;
+    Rec4 *pos4, *vel4, *gas4;
+    float4 *srch;               /* FP32 search record {u_x, u_y, u_z, thr}: position in cell units, acceptance threshold */
     int *mat;
-    double *sig, *cmat, *rart;
+    Rec4 *ten;                  /* TEN_RECS records per particle (solid) */
     int *nbr, *noi;
 };
 

@@ -231,13 +231,31 @@ __global__ void k_cell_start(const int *keys, int n, const Domain *dom, int *cel
     for (int c = prev + 1; c <= cur; c++) cell_start[c] = s;
 }
 
-__global__ void k_gather(b200sph_view v, Sorted s)
+/* FP32 pre-filter of the neighbour search.  Positions are stored in cell units, u = (x - lo)/cell,
+ * rounded to FP32; a candidate is kept when its FP32 distance is below BOTH particles' thresholds
+ * thr = (h/cell)^2 + margin.  The margin bounds every rounding on the FP32 path, so the filter never
+ * rejects a pair the exact FP64 test accepts; the few extra survivors (a shell of relative width
+ * ~1e-4) are removed by the exact test in the first pair loop that walks the list (LIST_VALIDATE).
+ *   |u_hat - u| <= 2^-24 nc          (conversion; nc = cells along the longest axis)
+ *   |D_hat - D| <= delta = 2^-22 nc + 2^-22 (hc + 1)     per axis (two conversions + the subtraction)
+ *   |d_hat - d| <= 2 sqrt(3) hc delta + 3 delta^2 + 2^-20 hc^2   for d <= hc^2 (hc = h/cell) */
+__device__ __forceinline__ float search_threshold(double h, const Domain &d)
+{
+    const double ncm = (double)max(d.nc[0], max(d.nc[1], d.nc[2]));
+    const double hc = h * d.cell_inv;
+    const double delta = 2.384185791015625e-07 * (ncm + hc + 1.0);
+    const double margin = 3.4641016151377544 * hc * delta + 3.0 * delta * delta + 9.5367431640625e-07 * hc * hc;
+    return __double2float_ru((hc * hc + 2.0 * margin) * 1.000001);
+}
+
+__global__ void k_gather(b200sph_view v, Sorted s, const Domain *dom)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= s.n) return;
     const int i = s.perm[k];
+    const Domain &d = *dom;
     const b200sph_particle_arrays &p = v.p;
-    double4 a, b;
+    Rec4 a, b;
     a.x = p.x[i]; b.x = p.vx[i];
 #if DIM > 1
     a.y = p.y[i]; b.y = p.vy[i];
@@ -251,15 +269,23 @@ __global__ void k_gather(b200sph_view v, Sorted s)
 #endif
     a.w = p.h[i];
     b.w = p.m[i];
-    s.pos4[k] = a;
-    s.vel4[k] = b;
-    s.mat[k] = v.p_rhs.materialId[i];
+    st_rec(&s.pos4[k], a);
+    st_rec(&s.vel4[k], b);
+    const int matId = v.p_rhs.materialId[i];
+    s.mat[k] = matId;
+    float4 f;
+    f.x = (float)((a.x - d.lo[0]) * d.cell_inv);
+    f.y = (DIM > 1) ? (float)((a.y - d.lo[1]) * d.cell_inv) : 0.0f;
+    f.z = (DIM > 2) ? (float)((a.z - d.lo[2]) * d.cell_inv) : 0.0f;
+    /* deactivated particles are never anybody's neighbour (src/tree.cu:845-847) */
+    f.w = (matId == EOS_TYPE_IGNORE) ? -1.0f : search_threshold(a.w, d);
+    s.srch[k] = f;
 }
 
 /* ------------------------------------------------------------------ k_neighbours
  * Membership: d < h_i^2 && d < h_j^2, j != i, materialId[j] != IGNORE, with d accumulated as the
  * reference's compiled code does (src/tree.cu:851-865: mul, then one fma per further axis). */
-__device__ __forceinline__ double pair_d2(const double4 &a, const double4 &b, double &dx, double &dy, double &dz)
+__device__ __forceinline__ double pair_d2(const Rec4 &a, const Rec4 &b, double &dx, double &dy, double &dz)
 {
     dx = a.x - b.x;
     double d = __dmul_rn(dx, dx);
@@ -280,36 +306,42 @@ __device__ __forceinline__ double pair_d2(const double4 &a, const double4 &b, do
 
 #define NBR_SLOT(s, k) ((((size_t)((s) / NBR_TILE)) * MAX_NUM_INTERACTIONS + (k)) * NBR_TILE + ((s) % NBR_TILE))
 
-__global__ void __launch_bounds__(128)
-k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags)
+struct Stencil {
+    int x0, x1, y0, y1, z0, z1;
+};
+
+__device__ __forceinline__ Stencil stencil_of(const Rec4 &pi, const Domain &d)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_targets) return;
-    const Domain &d = *dom;
-    const double4 pi = s.pos4[k];
-    const double h2 = __dmul_rn(pi.w, pi.w);
+    Stencil st;
     const int reach = (int)(pi.w * d.cell_inv + 1e-9) + 1;
     const int cx = cell_coord(pi.x, d.lo[0], d.cell_inv, d.nc[0]);
-    const int x0 = max(cx - reach, 0), x1 = min(cx + reach, d.nc[0] - 1);
+    st.x0 = max(cx - reach, 0); st.x1 = min(cx + reach, d.nc[0] - 1);
 #if DIM > 1
     const int cy = cell_coord(pi.y, d.lo[1], d.cell_inv, d.nc[1]);
-    const int y0 = max(cy - reach, 0), y1 = min(cy + reach, d.nc[1] - 1);
+    st.y0 = max(cy - reach, 0); st.y1 = min(cy + reach, d.nc[1] - 1);
 #else
-    const int y0 = 0, y1 = 0;
+    st.y0 = 0; st.y1 = 0;
 #endif
 #if DIM > 2
     const int cz = cell_coord(pi.z, d.lo[2], d.cell_inv, d.nc[2]);
-    const int z0 = max(cz - reach, 0), z1 = min(cz + reach, d.nc[2] - 1);
+    st.z0 = max(cz - reach, 0); st.z1 = min(cz + reach, d.nc[2] - 1);
 #else
-    const int z0 = 0, z1 = 0;
+    st.z0 = 0; st.z1 = 0;
 #endif
+    return st;
+}
+
+/* exact FP64 scan; only used for a particle whose pre-filtered candidates do not fit the list */
+__device__ __noinline__ int neighbours_exact(const Sorted &s, const Domain &d, int k, const Rec4 &pi, const Stencil &st)
+{
+    const double h2 = __dmul_rn(pi.w, pi.w);
     int cnt = 0;
-    for (int z = z0; z <= z1; z++)
-        for (int y = y0; y <= y1; y++) {
+    for (int z = st.z0; z <= st.z1; z++)
+        for (int y = st.y0; y <= st.y1; y++) {
             const int row = d.nc[0] * (y + d.nc[1] * z);
-            const int jb = s.cell_start[row + x0], je = s.cell_start[row + x1 + 1];
+            const int jb = s.cell_start[row + st.x0], je = s.cell_start[row + st.x1 + 1];
             for (int j = jb; j < je; j++) {
-                const double4 pj = s.pos4[j];
+                const Rec4 pj = ld_rec(&s.pos4[j]);
                 double dx, dy, dz;
                 const double dd = pair_d2(pi, pj, dx, dy, dz);
                 if (dd < h2 && dd < __dmul_rn(pj.w, pj.w) && j != k && s.mat[j] != EOS_TYPE_IGNORE) {
@@ -318,58 +350,174 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags)
                 }
             }
         }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(128)
+k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_targets) return;
+    const Domain &d = *dom;
+    const Rec4 pi = ld_rec(&s.pos4[k]);
+    const float4 si = s.srch[k];
+    const float thr_i = search_threshold(pi.w, d);   /* srch.w is -1 for a deactivated target, which still collects neighbours */
+    const Stencil st = stencil_of(pi, d);
+    int cnt = 0;
+    for (int z = st.z0; z <= st.z1; z++)
+        for (int y = st.y0; y <= st.y1; y++) {
+            const int row = d.nc[0] * (y + d.nc[1] * z);
+            const int jb = s.cell_start[row + st.x0], je = s.cell_start[row + st.x1 + 1];
+#pragma unroll 4
+            for (int j = jb; j < je; j++) {
+                const float4 c = __ldg(&s.srch[j]);
+                const float dx = si.x - c.x;
+                float dd = dx * dx;
+#if DIM > 1
+                const float dy = si.y - c.y;
+                dd = fmaf(dy, dy, dd);
+#endif
+#if DIM > 2
+                const float dz = si.z - c.z;
+                dd = fmaf(dz, dz, dd);
+#endif
+                if (dd < thr_i && dd < c.w && j != k) {
+                    if (cnt < MAX_NUM_INTERACTIONS) s.nbr[NBR_SLOT(k, cnt)] = j;
+                    cnt++;
+                }
+            }
+        }
+    if (cnt > MAX_NUM_INTERACTIONS) {
+        /* more survivors than list slots: decide with the exact test (the reference asserts on the exact count) */
+        cnt = neighbours_exact(s, d, k, pi, st);
+        if (cnt >= MAX_NUM_INTERACTIONS) {
+            atomicMin(&flags[0], s.perm[k]);
+            cnt = MAX_NUM_INTERACTIONS - 1;
+        }
+    }
+    s.noi[k] = cnt;   /* list slots in use; the exact count replaces it in the LIST_VALIDATE pass */
+}
+
+/* How a pair loop treats the list it walks:
+ *   LIST_EXACT     entries are exact neighbours (an earlier pass validated the list)
+ *   LIST_VALIDATE  first walk after the search: apply the exact FP64 membership test, compact the
+ *                  list in place, store the exact count, flag an overflow
+ *   LIST_CHECK     apply the exact test but leave the list alone (a pass that does not visit every particle) */
+enum { LIST_EXACT = 0, LIST_VALIDATE = 1, LIST_CHECK = 2 };
+
+__device__ __forceinline__ bool pair_is_neighbour(double r2, double h2_i, const Rec4 &pj)
+{
+    return r2 < h2_i && r2 < __dmul_rn(pj.w, pj.w);
+}
+
+/* walk a list only to validate it (particles whose pair loop is skipped) */
+__device__ __noinline__ int validate_only(const Sorted &s, int k, const Rec4 &pi, int nslots)
+{
+    const double h2 = __dmul_rn(pi.w, pi.w);
+    int cnt = 0;
+    for (int q = 0; q < nslots; q++) {
+        const int j = s.nbr[NBR_SLOT(k, q)];
+        const Rec4 pj = ld_rec(&s.pos4[j]);
+        double dx, dy, dz;
+        const double r2 = pair_d2(pi, pj, dx, dy, dz);
+        if (!pair_is_neighbour(r2, h2, pj)) continue;
+        if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
+        cnt++;
+    }
+    return cnt;
+}
+
+__device__ __forceinline__ int finish_validate(const Sorted &s, int k, int cnt, int *flags)
+{
     if (cnt >= MAX_NUM_INTERACTIONS) { /* the reference asserts here (src/tree.cu:917) */
         atomicMin(&flags[0], s.perm[k]);
         cnt = MAX_NUM_INTERACTIONS - 1;
     }
     s.noi[k] = cnt;
-    atomicMax(&flags[1], cnt);
+    return cnt;
+}
+
+/* max and sum of the exact interaction counts (stats; one atomic pair per block) */
+__global__ void __launch_bounds__(256) k_list_stats(Sorted s, int *flags)
+{
+    int mx = 0, sum = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < s.n; k += gridDim.x * blockDim.x) {
+        const int c = s.noi[k];
+        mx = max(mx, c);
+        sum += c;
+    }
+    mx = __reduce_max_sync(FULL_MASK, mx);
+    sum = __reduce_add_sync(FULL_MASK, sum);
+    __shared__ int smx[8], ssum[8];
+    if ((threadIdx.x & 31) == 0) { smx[threadIdx.x >> 5] = mx; ssum[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long tot = 0;
+        for (int w = 0; w < 8; w++) { mx = max(mx, smx[w]); tot += ssum[w]; }
+        atomicMax(&flags[1], mx);
+        atomicAdd(reinterpret_cast<unsigned long long *>(flags + 2), (unsigned long long)tot);
+    }
 }
 
 /* ------------------------------------------------------------------ k_density */
+template <int MODE>
 __global__ void __launch_bounds__(128)
-k_density(Sorted s, b200sph_view v, double *rho_sorted, int n_targets)
+k_density(Sorted s, b200sph_view v, double *rho_sorted, int n_targets, int *flags)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_targets) return;
     const int matId = s.mat[k];
     const int i = s.perm[k];
+    const Rec4 pi = ld_rec(&s.pos4[k]);
+    const int nslots = s.noi[k];
 #if INTEGRATE_DENSITY
     if (mat_ignored(matId) || c_mat[matId].density_via_kernel_sum < 1) {
         rho_sorted[k] = v.p.rho[i];
+        if (MODE == LIST_VALIDATE) finish_validate(s, k, validate_only(s, k, pi, nslots), flags);
         return;
     }
 #endif
-    const double4 pi = s.pos4[k];
-    const double hinv_i = 1.0 / pi.w;
-    double rho = s.vel4[k].w * cubic_spline_w(0.0, hinv_i);
-    if (!mat_ignored(matId)) {
-        const int noi = s.noi[k];
-        for (int q = 0; q < noi; q++) {
-            const int j = s.nbr[NBR_SLOT(k, q)];
-            if (mat_ignored(s.mat[j])) continue;
-            const double4 pj = s.pos4[j];
-            double dx, dy, dz, W, g;
-            const double r2 = pair_d2(pi, pj, dx, dy, dz);
-#if AVERAGE_KERNELS
-            /* W = (W(h_i) + W(h_j))/2.  The reference evaluates the second kernel with the
-             * smoothing length of the particle whose index equals the LOOP COUNTER
-             * (src/density.cu:130-138); identical whenever h is uniform, which holds for every
-             * config that sets AVERAGE_KERNELS (fixed sml per material). */
-            cubic_spline(r2, hinv_i, W, g);
-            if (pj.w != pi.w) {
-                double Wj;
-                cubic_spline(r2, 1.0 / pj.w, Wj, g);
-                W = 0.5 * (W + Wj);
-            }
-#elif VARIABLE_SML || INTEGRATE_SML
-            cubic_spline(r2, 1.0 / (0.5 * (pi.w + pj.w)), W, g);
-#else
-            cubic_spline(r2, hinv_i, W, g);
-#endif
-            rho = fma(s.vel4[j].w, W, rho);
-        }
+    if (mat_ignored(matId)) {
+        const double rho = ld_rec(&s.vel4[k]).w * cubic_spline_w(0.0, 1.0 / pi.w);
+        rho_sorted[k] = rho;
+        v.p.rho[i] = rho;
+        if (MODE == LIST_VALIDATE) finish_validate(s, k, validate_only(s, k, pi, nslots), flags);
+        return;
     }
+    const double hinv_i = 1.0 / pi.w;
+    const double h2_i = __dmul_rn(pi.w, pi.w);
+    double rho = ld_rec(&s.vel4[k]).w * cubic_spline_w(0.0, hinv_i);
+    int cnt = 0;
+    for (int q = 0; q < nslots; q++) {
+        const int j = s.nbr[NBR_SLOT(k, q)];
+        const Rec4 pj = ld_rec(&s.pos4[j]);
+        double dx, dy, dz, W, g;
+        const double r2 = pair_d2(pi, pj, dx, dy, dz);
+        if (MODE != LIST_EXACT && !pair_is_neighbour(r2, h2_i, pj)) continue;
+        if (MODE == LIST_VALIDATE) {
+            if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
+            cnt++;
+        }
+        if (s.any_eos_ignore && mat_ignored(s.mat[j])) continue;
+#if AVERAGE_KERNELS
+        /* W = (W(h_i) + W(h_j))/2.  The reference evaluates the second kernel with the
+         * smoothing length of the particle whose index equals the LOOP COUNTER
+         * (src/density.cu:130-138); identical whenever h is uniform, which holds for every
+         * config that sets AVERAGE_KERNELS (fixed sml per material). */
+        cubic_spline(r2, hinv_i, W, g);
+        if (pj.w != pi.w) {
+            double Wj;
+            cubic_spline(r2, 1.0 / pj.w, Wj, g);
+            W = 0.5 * (W + Wj);
+        }
+#elif VARIABLE_SML || INTEGRATE_SML
+        cubic_spline(r2, 1.0 / (0.5 * (pi.w + pj.w)), W, g);
+#else
+        cubic_spline(r2, hinv_i, W, g);
+#endif
+        rho = fma(s.vel4[j].w, W, rho);
+    }
+    if (MODE == LIST_VALIDATE) finish_validate(s, k, cnt, flags);
     rho_sorted[k] = rho;
     v.p.rho[i] = rho;
 }
@@ -511,7 +659,7 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
     double rho = use_rho_sorted ? rho_sorted[k] : p.rho[i];
 
     if (matId < 0) { /* deactivated particle: never a neighbour, keep the records finite */
-        s.gas4[k] = make_double4(0.0, 0.0, rho, 0.0);
+        st_rec(&s.gas4[k], Rec4{0.0, 0.0, rho, 0.0});
         return;
     }
     const MatParams &M = c_mat[matId];
@@ -525,7 +673,7 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
     const double cs = eos_soundspeed(M, rho, e, p.p[i], alpha_in, p.cs[i]);
     p.cs[i] = cs;
     if (M.eos == EOS_TYPE_IGNORE) {
-        s.gas4[k] = make_double4(0.0, cs, rho, m / rho);
+        st_rec(&s.gas4[k], Rec4{0.0, cs, rho, m / rho});
         return;
     }
     PorousOut po;
@@ -645,6 +793,9 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
     if (pres < 0.0) ptmp = (1.0 - damage) * pres;
 #endif
     const double irho2 = 1.0 / (rho * rho);
+    double ten[4 * TEN_RECS];
+#pragma unroll
+    for (int c = 0; c < 4 * TEN_RECS; c++) ten[c] = 0.0;
     double sigma[DIM][DIM];
 #pragma unroll
     for (int a = 0; a < DIM; a++)
@@ -658,7 +809,7 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
             if (a == b) sg -= ptmp;
             sigma[a][b] = sg;
             pr.sigma[(size_t)i * DD + a * DIM + b] = sg;
-            s.sig[(size_t)k * DD + a * DIM + b] = sg * irho2;
+            ten[ten_sig(a, b)] = sg * irho2;
         }
 #if ARTIFICIAL_STRESS
     /* compute_artificial_stress, src/artificial_stress.cu:34-100: R = -eps * sigma_+ in principal axes */
@@ -677,46 +828,57 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
                     r += V[c][a] * rc * V[c][b];
                 }
                 pr.R[(size_t)i * DD + a * DIM + b] = r;
-                s.rart[(size_t)k * DD + a * DIM + b] = r * irho2;
+                if (a <= b) ten[ten_r(a, b)] = r * irho2;
             }
     }
 #endif
     p.p[i] = pres;
-    s.gas4[k] = make_double4(irho2, cs, rho, m / rho);
+    st_rec(&s.gas4[k], Rec4{irho2, cs, rho, m / rho});
+#pragma unroll
+    for (int r = 0; r < TEN_RECS; r++)
+        st_rec(&s.ten[(size_t)k * TEN_RECS + r], Rec4{ten[4 * r], ten[4 * r + 1], ten[4 * r + 2], ten[4 * r + 3]});
 #else /* HYDRO */
     p.p[i] = pres;
-    s.gas4[k] = make_double4(pres / (rho * rho), cs, rho, m / rho);
+    st_rec(&s.gas4[k], Rec4{pres / (rho * rho), cs, rho, m / rho});
 #endif
 }
 
 #if TENSORIAL_CORRECTION
 /* ------------------------------------------------------------------ k_correction */
+template <int MODE>
 __global__ void __launch_bounds__(128)
-k_correction(Sorted s, b200sph_view v, int n_targets)
+k_correction(Sorted s, b200sph_view v, int n_targets, int *flags)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_targets) return;
     const int i = s.perm[k];
+    const Rec4 pi = ld_rec(&s.pos4[k]);
+    const int nslots = s.noi[k];
     double C[DIM][DIM];
 #pragma unroll
     for (int a = 0; a < DIM; a++)
 #pragma unroll
         for (int b = 0; b < DIM; b++) C[a][b] = (a == b) ? 1.0 : 0.0;
     if (!mat_ignored(s.mat[k])) {
-        const double4 pi = s.pos4[k];
         const double hinv = 1.0 / pi.w;   /* h_i, not the pair mean (src/kernel.cu:637) */
+        const double h2_i = __dmul_rn(pi.w, pi.w);
         double A[DIM][DIM];
 #pragma unroll
         for (int a = 0; a < DIM; a++)
 #pragma unroll
             for (int b = 0; b < DIM; b++) A[a][b] = 0.0;
-        const int noi = s.noi[k];
-        for (int q = 0; q < noi; q++) {
+        int cnt = 0;
+        for (int q = 0; q < nslots; q++) {
             const int j = s.nbr[NBR_SLOT(k, q)];
-            if (mat_ignored(s.mat[j])) continue;
-            const double4 pj = s.pos4[j];
+            const Rec4 pj = ld_rec(&s.pos4[j]);
             double dr[3], W, g;
             const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
+            if (MODE != LIST_EXACT && !pair_is_neighbour(r2, h2_i, pj)) continue;
+            if (MODE == LIST_VALIDATE) {
+                if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
+                cnt++;
+            }
+            if (s.any_eos_ignore && mat_ignored(s.mat[j])) continue;
 #if AVERAGE_KERNELS
             cubic_spline(r2, hinv, W, g);
             if (pj.w != pi.w) {
@@ -728,11 +890,19 @@ k_correction(Sorted s, b200sph_view v, int n_targets)
             cubic_spline(r2, hinv, W, g);
 #endif
             const double w = s.gas4[j].w * g;   /* (m_j/rho_j) * dW/dr / r */
+            /* A is symmetric: accumulate the upper triangle only */
 #pragma unroll
-            for (int a = 0; a < DIM; a++)
+            for (int a = 0; a < DIM; a++) {
+                const double wa = -w * dr[a];
 #pragma unroll
-                for (int b = 0; b < DIM; b++) A[a][b] = fma(-w * dr[a], dr[b], A[a][b]);
+                for (int b = a; b < DIM; b++) A[a][b] = fma(wa, dr[b], A[a][b]);
+            }
         }
+        if (MODE == LIST_VALIDATE) finish_validate(s, k, cnt, flags);
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < a; b++) A[a][b] = A[b][a];
         sym_pinv(A, C);
 #if DIM == 2
         const double det = C[0][0] * C[1][1] - C[0][1] * C[1][0];
@@ -751,20 +921,24 @@ k_correction(Sorted s, b200sph_view v, int n_targets)
 #pragma unroll
                 for (int b = 0; b < DIM; b++) C[a][b] = (a == b) ? 1.0 : 0.0;
         }
+    } else if (MODE == LIST_VALIDATE) {
+        finish_validate(s, k, validate_only(s, k, pi, nslots), flags);
     }
+    double *ten = reinterpret_cast<double *>(s.ten + (size_t)k * TEN_RECS);
 #pragma unroll
     for (int a = 0; a < DIM; a++)
 #pragma unroll
         for (int b = 0; b < DIM; b++) {
-            s.cmat[(size_t)k * DD + a * DIM + b] = C[a][b];
+            if (a <= b) ten[ten_c(a, b)] = C[a][b];
             v.p_rhs.tensorialCorrectionMatrix[(size_t)i * DD + a * DIM + b] = C[a][b];
         }
 }
 #endif
 
 /* ------------------------------------------------------------------ k_forces */
+template <int MODE>
 __global__ void __launch_bounds__(128)
-k_forces(Sorted s, b200sph_view v, int n_targets)
+k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_targets) return;
@@ -772,10 +946,10 @@ k_forces(Sorted s, b200sph_view v, int n_targets)
     const int matId = s.mat[k];
     const b200sph_particle_arrays &p = v.p;
     const b200sph_particle_arrays &pr = v.p_rhs;
-    const double4 pi = s.pos4[k];
-    const double4 vi = s.vel4[k];
-    const int noi = s.noi[k];
-    p.noi[i] = noi;
+    const Rec4 pi = ld_rec(&s.pos4[k]);
+    const Rec4 vi = ld_rec(&s.vel4[k]);
+    const int nslots = s.noi[k];
+    int noi = nslots;
 
     const bool active = !(matId == BOUNDARY_PARTICLE_ID || mat_ignored(matId)) && i < v.n_real;
     double acc[3] = {0.0, 0.0, 0.0}, drhodt = 0.0, dedt = 0.0, dhdt = 0.0, muijmax = 0.0;
@@ -795,27 +969,38 @@ k_forces(Sorted s, b200sph_view v, int n_targets)
 #endif
 #endif
 
-    if (active && noi > 0) {
+    if (active && nslots > 0) {
         const MatParams &M = c_mat[matId];
-        const double4 gi = s.gas4[k];
+        const Rec4 gi = ld_rec(&s.gas4[k]);
+        const double h2_i = __dmul_rn(pi.w, pi.w);
+        int cnt = 0;
+        (void)h2_i; (void)cnt;
         const double rho_i = gi.z;
         (void)rho_i;
 #if ARTIFICIAL_VISCOSITY
         const double av_alpha = M.av_alpha, av_beta = M.av_beta;
 #endif
 #if SOLID
+        {
+            double ti[4 * TEN_RECS];
 #pragma unroll
-        for (int a = 0; a < DIM; a++)
+            for (int r = 0; r < TEN_RECS; r++) {
+                const Rec4 t = ld_rec(&s.ten[(size_t)k * TEN_RECS + r]);
+                ti[4 * r] = t.x; ti[4 * r + 1] = t.y; ti[4 * r + 2] = t.z; ti[4 * r + 3] = t.w;
+            }
 #pragma unroll
-            for (int b = 0; b < DIM; b++) {
-                sig_i[a][b] = s.sig[(size_t)k * DD + a * DIM + b];
+            for (int a = 0; a < DIM; a++)
+#pragma unroll
+                for (int b = 0; b < DIM; b++) {
+                    sig_i[a][b] = ti[ten_sig(a, b)];
 #if TENSORIAL_CORRECTION
-                Ci[a][b] = s.cmat[(size_t)k * DD + a * DIM + b];
+                    Ci[a][b] = ti[ten_c(a, b)];
 #endif
 #if ARTIFICIAL_STRESS
-                Ri[a][b] = s.rart[(size_t)k * DD + a * DIM + b];
+                    Ri[a][b] = ti[ten_r(a, b)];
 #endif
-            }
+                }
+        }
         const double m_over_rho_i_unit = 1.0 / rho_i;   /* strain rate uses m_j / rho_i (src/internal_forces.cu:476) */
 #endif
 #if !(VARIABLE_SML || INTEGRATE_SML)
@@ -824,14 +1009,27 @@ k_forces(Sorted s, b200sph_view v, int n_targets)
 #if ARTIFICIAL_STRESS
         const double w_ref_dist = M.mean_particle_distance;
 #endif
-        for (int q = 0; q < noi; q++) {
+        for (int q = 0; q < nslots; q++) {
             const int j = s.nbr[NBR_SLOT(k, q)];
-            if (mat_ignored(s.mat[j])) continue;
-            const double4 pj = s.pos4[j];
-            const double4 vj = s.vel4[j];
-            const double4 gj = s.gas4[j];
+            const Rec4 pj = ld_rec(&s.pos4[j]);
             double dr[3], dv[3], W, g;
             const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
+            if (MODE != LIST_EXACT && !pair_is_neighbour(r2, h2_i, pj)) continue;
+            if (MODE == LIST_VALIDATE) {
+                if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
+                cnt++;
+            }
+            if (s.any_eos_ignore && mat_ignored(s.mat[j])) continue;
+            const Rec4 vj = ld_rec(&s.vel4[j]);
+            const Rec4 gj = ld_rec(&s.gas4[j]);
+#if SOLID
+            double tj[4 * TEN_RECS];
+#pragma unroll
+            for (int r = 0; r < TEN_RECS; r++) {
+                const Rec4 t = ld_rec(&s.ten[(size_t)j * TEN_RECS + r]);
+                tj[4 * r] = t.x; tj[4 * r + 1] = t.y; tj[4 * r + 2] = t.z; tj[4 * r + 3] = t.w;
+            }
+#endif
             dv[0] = vi.x - vj.x; dv[1] = vi.y - vj.y; dv[2] = vi.z - vj.z;
 #if VARIABLE_SML || INTEGRATE_SML
             const double hbar = 0.5 * (pi.w + pj.w);
@@ -851,15 +1049,15 @@ k_forces(Sorted s, b200sph_view v, int n_targets)
             double gci[DIM], gcj[DIM], gsym[DIM];
 #pragma unroll
             for (int a = 0; a < DIM; a++) {
-                double ti = 0.0, tj = 0.0;
+                double tci = 0.0, tcj = 0.0;
 #pragma unroll
                 for (int b = 0; b < DIM; b++) {
-                    ti = fma(Ci[a][b], gw[b], ti);
-                    tj = fma(s.cmat[(size_t)j * DD + a * DIM + b], gw[b], tj);
+                    tci = fma(Ci[a][b], gw[b], tci);
+                    tcj = fma(tj[ten_c(a, b)], gw[b], tcj);
                 }
-                gci[a] = ti;
-                gcj[a] = tj;
-                gsym[a] = 0.5 * (ti + tj);
+                gci[a] = tci;
+                gcj[a] = tcj;
+                gsym[a] = 0.5 * (tci + tcj);
             }
 #else
             const double *gsym = gw;
@@ -907,10 +1105,10 @@ k_forces(Sorted s, b200sph_view v, int n_targets)
 #pragma unroll
                     for (int b = 0; b < DIM; b++) {
 #if TENSORIAL_CORRECTION
-                        t = fma(s.sig[(size_t)j * DD + a * DIM + b], gcj[b], t);
+                        t = fma(tj[ten_sig(a, b)], gcj[b], t);
                         t = fma(sig_i[a][b], gci[b], t);
 #else
-                        t = fma(s.sig[(size_t)j * DD + a * DIM + b] + sig_i[a][b], gw[b], t);
+                        t = fma(tj[ten_sig(a, b)] + sig_i[a][b], gw[b], t);
 #endif
                     }
                     aj[a] = mj * t;
@@ -929,9 +1127,9 @@ k_forces(Sorted s, b200sph_view v, int n_targets)
                         for (int b = 0; b < DIM; b++) {
 #if TENSORIAL_CORRECTION
                             t = fma(Ri[a][b], gci[b], t);
-                            t = fma(s.rart[(size_t)j * DD + a * DIM + b], gcj[b], t);
+                            t = fma(tj[ten_r(a, b)], gcj[b], t);
 #else
-                            t = fma(Ri[a][b] + s.rart[(size_t)j * DD + a * DIM + b], gw[b], t);
+                            t = fma(Ri[a][b] + tj[ten_r(a, b)], gw[b], t);
 #endif
                         }
                         const double art = mj * artf * t;
@@ -984,7 +1182,11 @@ k_forces(Sorted s, b200sph_view v, int n_targets)
             dhdt = fma(-(1.0 / DIM) * pi.w * gj.w, vvnablaW, dhdt);
 #endif
         }
+        if (MODE == LIST_VALIDATE) noi = finish_validate(s, k, cnt, flags);
+    } else if (MODE == LIST_VALIDATE) {
+        noi = finish_validate(s, k, validate_only(s, k, pi, nslots), flags);
     }
+    p.noi[i] = noi;
 
     /* ---------------- per-particle epilogue: everything the integrators read, in caller order */
     if (!active) {
@@ -1303,7 +1505,7 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     /* library plumbing (not counted in kernel_launches) */
     CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, h->cub_tmp_bytes, h->keys_in, s.keys, h->idx_in, s.perm, n, 0, h->sort_bits, st));
     k_cell_start<<<blocks_for(n + 1, 256), 256, 0, st>>>(s.keys, n, h->d_domain, s.cell_start);
-    k_gather<<<blocks_for(n, 256), 256, 0, st>>>(v, s);
+    k_gather<<<blocks_for(n, 256), 256, 0, st>>>(v, s, h->d_domain);
     launches += 2;
     CU(cudaEventRecord(h->ev[1], st));
 
@@ -1311,11 +1513,20 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     launches++;
     CU(cudaEventRecord(h->ev[2], st));
 
-    /* kernel-sum density: always without INTEGRATE_DENSITY, else only for materials that ask for it */
+    /* The search leaves FP32-pre-filtered lists; the first pair loop that visits EVERY particle applies
+     * the exact test and compacts them (LIST_VALIDATE), later loops trust them (LIST_EXACT).
+     * kernel-sum density: always without INTEGRATE_DENSITY, else only for materials that ask for it
+     * (then it does not visit every particle and only checks, LIST_CHECK). */
     const int use_rho_sorted = h->kernel_sum_density;
     double *rho_sorted = h->rho_sorted;
+    int validated = 0;
     if (use_rho_sorted) {
-        k_density<<<blocks_for(n_targets, T), T, 0, st>>>(s, v, rho_sorted, n_targets);
+#if INTEGRATE_DENSITY
+        k_density<LIST_CHECK><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, rho_sorted, n_targets, h->d_flags);
+#else
+        k_density<LIST_VALIDATE><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, rho_sorted, n_targets, h->d_flags);
+        validated = 1;
+#endif
         launches++;
     }
     CU(cudaEventRecord(h->ev[3], st));
@@ -1324,12 +1535,16 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     launches++;
     CU(cudaEventRecord(h->ev[4], st));
 #if TENSORIAL_CORRECTION
-    k_correction<<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets);
+    if (validated) k_correction<LIST_EXACT><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets, h->d_flags);
+    else k_correction<LIST_VALIDATE><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets, h->d_flags);
+    validated = 1;
     launches++;
 #endif
     CU(cudaEventRecord(h->ev[5], st));
-    k_forces<<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets);
-    launches++;
+    if (validated) k_forces<LIST_EXACT><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets, h->d_flags);
+    else k_forces<LIST_VALIDATE><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets, h->d_flags);
+    k_list_stats<<<min(blocks_for(n, 256), 148 * 4), 256, 0, st>>>(s, h->d_flags);
+    launches += 2;
     CU(cudaEventRecord(h->ev[6], st));
 
     h->stats.gravity_recomputed = 0;
@@ -1350,6 +1565,7 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     S.n_cells = h->h_domain.n_cells;
     S.cell_size = h->h_domain.cell;
     S.max_noi = flags[1];
+    S.total_noi = (int64_t)(((unsigned long long)(unsigned int)flags[3] << 32) | (unsigned int)flags[2]);
     cudaEventElapsedTime(&S.ms_total, h->ev[0], h->ev[7]);
     cudaEventElapsedTime(&S.ms_sort, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&S.ms_neighbours, h->ev[1], h->ev[2]);
