@@ -40,7 +40,7 @@ def build_one(config: str, force: bool = False, verbose: bool = False, config_di
     cdir = config_dir or os.path.join(HERE, "configs", config)
     objdir = os.path.join(LIBDIR, "obj", config)
     os.makedirs(objdir, exist_ok=True)
-    common = ["-I", cdir, "-I", CSRC, f'-DB200SPH_CONFIG_NAME="{config}"']
+    common = ["-I", cdir, "-I", CSRC, f'-DB200SPH_CONFIG_NAME="{config}"', *os.environ.get("B200SPH_EXTRA_FLAGS", "").split()]
     objs = []
     for src in CU_SOURCES:
         obj = os.path.join(objdir, src + ".o")

@@ -103,7 +103,7 @@ extern "C" int b200sph_create(b200sph_handle **out, int n_max, int device, uint6
     ALLOC(s.noi, n);
     ALLOC(h->keys_in, n); ALLOC(h->idx_in, n);
     ALLOC(h->rho_sorted, n);
-    ALLOC(h->block_partials, 148 * 4 * 8 + 8);
+    ALLOC(h->block_partials, 148 * 4 * 16 + 16);
     ALLOC(h->block_counter, 4);
     ALLOC(h->d_flags, 8);
     ALLOC(h->d_domain, 1);
@@ -129,6 +129,13 @@ extern "C" int b200sph_create(b200sph_handle **out, int n_max, int device, uint6
     }
     h->flag_force_gravity_calc = 0;
     h->gravity_index = 0;
+    h->forces_threads = SOLID ? 64 : 128;
+    {
+        /* tuning knob for profiling sessions; the default above is what ships */
+        const char *env = getenv("B200SPH_FORCES_THREADS");
+        const int t = env ? atoi(env) : 0;
+        if (t == 32 || t == 64 || t == 96 || t == 128) h->forces_threads = t;
+    }
     *out = h;
     return B200SPH_OK;
 }

@@ -127,6 +127,7 @@ struct b200sph_handle {
     double *rho_sorted;
     double *aneos_buf;          /* device copy of the tabulated-EOS payload */
     int n_owned;
+    int forces_threads;         /* block size of k_forces: small blocks keep more warps resident at high register counts */
     int have_global_domain;
     double global_lo[3], global_hi[3];
     /* host-view staging (b200sph_rhs_eval_host) */

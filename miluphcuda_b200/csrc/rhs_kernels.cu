@@ -61,8 +61,8 @@ __device__ __forceinline__ double coord_of(const b200sph_particle_arrays &p, int
 }
 
 /* ------------------------------------------------------------------ k_prepare
- * values per block: min[3], max[3], sum h, max h */
-#define PREP_VALUES 8
+ * values per block: min[3], max[3], sum h, max h, min h */
+#define PREP_VALUES 9
 #define PREP_THREADS 256
 
 __global__ void __launch_bounds__(PREP_THREADS)
@@ -71,7 +71,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
 {
     const b200sph_particle_arrays &p = v.p;
     const b200sph_particle_arrays &pr = v.p_rhs;
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, hsum = 0.0, hmax = 0.0;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, hsum = 0.0, hmax = 0.0, hmin = 1e300;
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
         const int matId = pr.materialId[i];
@@ -99,6 +99,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
         const double h = p.h[i];
         hsum += h;
         hmax = fmax(hmax, h);
+        hmin = fmin(hmin, h);
 #pragma unroll
         for (int a = 0; a < DIM; a++) {
             const double c = coord_of(p, i, a);
@@ -118,6 +119,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
     }
     vals[6] = warp_sum(hsum);
     vals[7] = warp_max(hmax);
+    vals[8] = warp_min(hmin);
     if (lane == 0)
 #pragma unroll
         for (int k = 0; k < PREP_VALUES; k++) sh[warp][k] = vals[k];
@@ -130,6 +132,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
             }
             sh[0][6] += sh[w][6];
             sh[0][7] = fmax(sh[0][7], sh[w][7]);
+            sh[0][8] = fmin(sh[0][8], sh[w][8]);
         }
         for (int k = 0; k < PREP_VALUES; k++) partials[blockIdx.x * PREP_VALUES + k] = sh[0][k];
         __threadfence();
@@ -151,6 +154,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
         }
         r[6] += q[6];
         r[7] = fmax(r[7], q[7]);
+        r[8] = fmin(r[8], q[8]);
     }
     *counter = 0;
     Domain d;
@@ -175,7 +179,11 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
     d.h_max = r[7];
     d.h_mean = r[6] / (double)v.n;
 #if VARIABLE_SML
-    double cell = fmin(d.h_max, 1.3 * d.h_mean) * 1.0001;
+    /* Cells as small as the smallest smoothing lengths: the bulk of a variable-resolution set sits at
+     * the finest resolution, and a cell edge of 1.3 h_mean made those particles test ~1200 candidates
+     * for ~35 neighbours (profiles/r01_ncu_full_impact_v1_summary.csv).  Coarse particles reach further
+     * (stencil_of) but live where cells are nearly empty.  Floored at h_mean/2 against outliers. */
+    double cell = fmin(d.h_max, fmax(r[8], 0.5 * d.h_mean)) * 1.0001;
 #else
     double cell = d.h_max * 1.0001;
 #endif
@@ -220,15 +228,30 @@ __global__ void k_cell_keys(b200sph_view v, const Domain *dom, int *keys, int *i
     idx[i] = i;
 }
 
-/* cell_start[c] = first sorted slot whose key >= c, for c in [0, n_cells] */
+/* cell_start[c] = first sorted slot whose key >= c, for c in [0, n_cells].  One thread per sorted slot
+ * fills the cells between its predecessor's key and its own; runs of empty cells longer than 32 (sparse
+ * ejecta, variable resolution) are filled by the whole warp instead of one lane. */
 __global__ void k_cell_start(const int *keys, int n, const Domain *dom, int *cell_start)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > n) return;
+    const int lane = threadIdx.x & 31;
     const int n_cells = dom->n_cells;
-    const int prev = (s == 0) ? -1 : keys[s - 1];
-    const int cur = (s == n) ? n_cells : keys[s];
-    for (int c = prev + 1; c <= cur; c++) cell_start[c] = s;
+    int prev = 0, cur = -1;
+    if (s <= n) {
+        prev = (s == 0) ? -1 : keys[s - 1];
+        cur = (s == n) ? n_cells : keys[s];
+    }
+    const bool long_run = cur - prev > 32;
+    if (!long_run)
+        for (int c = prev + 1; c <= cur; c++) cell_start[c] = s;
+    unsigned int todo = __ballot_sync(FULL_MASK, long_run);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int p0 = __shfl_sync(FULL_MASK, prev, src), c0 = __shfl_sync(FULL_MASK, cur, src);
+        const int s0 = __shfl_sync(FULL_MASK, s, src);
+        for (int c = p0 + 1 + lane; c <= c0; c += 32) cell_start[c] = s0;
+    }
 }
 
 /* FP32 pre-filter of the neighbour search.  Positions are stored in cell units, u = (x - lo)/cell,
@@ -363,7 +386,10 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags)
     const float4 si = s.srch[k];
     const float thr_i = search_threshold(pi.w, d);   /* srch.w is -1 for a deactivated target, which still collects neighbours */
     const Stencil st = stencil_of(pi, d);
+    /* The particle itself passes the filter (distance 0) and is stored like any survivor; the
+     * validating pair loop drops it.  That keeps the j != k comparison out of the candidate loop. */
     int cnt = 0;
+    int *slot = s.nbr + NBR_SLOT(k, 0);
     for (int z = st.z0; z <= st.z1; z++)
         for (int y = st.y0; y <= st.y1; y++) {
             const int row = d.nc[0] * (y + d.nc[1] * z);
@@ -381,10 +407,10 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags)
                 const float dz = si.z - c.z;
                 dd = fmaf(dz, dz, dd);
 #endif
-                if (dd < thr_i && dd < c.w && j != k) {
-                    if (cnt < MAX_NUM_INTERACTIONS) s.nbr[NBR_SLOT(k, cnt)] = j;
-                    cnt++;
-                }
+                const bool hit = dd < fminf(thr_i, c.w);
+                if (hit && cnt < MAX_NUM_INTERACTIONS) *slot = j;   /* predicated store, no divergent branch */
+                slot += hit ? NBR_TILE : 0;
+                cnt += hit ? 1 : 0;
             }
         }
     if (cnt > MAX_NUM_INTERACTIONS) {
@@ -420,7 +446,7 @@ __device__ __noinline__ int validate_only(const Sorted &s, int k, const Rec4 &pi
         const Rec4 pj = ld_rec(&s.pos4[j]);
         double dx, dy, dz;
         const double r2 = pair_d2(pi, pj, dx, dy, dz);
-        if (!pair_is_neighbour(r2, h2, pj)) continue;
+        if (j == k || !pair_is_neighbour(r2, h2, pj)) continue;
         if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
         cnt++;
     }
@@ -459,6 +485,40 @@ __global__ void __launch_bounds__(256) k_list_stats(Sorted s, int *flags)
     }
 }
 
+/* Everything a pair loop gathers about neighbour j.  The loops are software-pipelined: the list index
+ * is fetched two iterations ahead and the records one iteration ahead, so the dependent chain
+ * index -> records (two L2 round trips) overlaps the FP64 work of the current pair
+ * (profiles/r01_ncu_full_*_v1: 61 % of the stall samples of k_forces were long-scoreboard waits). */
+struct PairRecs {
+    Rec4 p, v, g;
+#if SOLID
+    Rec4 t[TEN_RECS];
+#endif
+};
+
+/* B200_PREFETCH_TENSORS: also fetch the solid tensor records one iteration ahead (costs 8*TEN_RECS registers) */
+#ifndef B200_PREFETCH_TENSORS
+#define B200_PREFETCH_TENSORS 0
+#endif
+
+__device__ __forceinline__ void load_tensor_recs(const Sorted &s, int j, PairRecs &r)
+{
+#if SOLID
+#pragma unroll
+    for (int c = 0; c < TEN_RECS; c++) r.t[c] = ld_rec(&s.ten[(size_t)j * TEN_RECS + c]);
+#endif
+}
+
+__device__ __forceinline__ void load_force_recs(const Sorted &s, int j, PairRecs &r)
+{
+    r.p = ld_rec(&s.pos4[j]);
+    r.v = ld_rec(&s.vel4[j]);
+    r.g = ld_rec(&s.gas4[j]);
+#if B200_PREFETCH_TENSORS
+    load_tensor_recs(s, j, r);
+#endif
+}
+
 /* ------------------------------------------------------------------ k_density */
 template <int MODE>
 __global__ void __launch_bounds__(128)
@@ -488,12 +548,26 @@ k_density(Sorted s, b200sph_view v, double *rho_sorted, int n_targets, int *flag
     const double h2_i = __dmul_rn(pi.w, pi.w);
     double rho = ld_rec(&s.vel4[k]).w * cubic_spline_w(0.0, hinv_i);
     int cnt = 0;
+    int j_next = 0, j_next2 = 0;
+    Rec4 pj_next = pi;
+    double mj_next = 0.0;
+    if (nslots > 0) {
+        j_next = s.nbr[NBR_SLOT(k, 0)];
+        j_next2 = s.nbr[NBR_SLOT(k, min(1, nslots - 1))];
+        pj_next = ld_rec(&s.pos4[j_next]);
+        mj_next = s.vel4[j_next].w;
+    }
     for (int q = 0; q < nslots; q++) {
-        const int j = s.nbr[NBR_SLOT(k, q)];
-        const Rec4 pj = ld_rec(&s.pos4[j]);
+        const int j = j_next;
+        const Rec4 pj = pj_next;
+        const double mj = mj_next;
+        j_next = j_next2;
+        j_next2 = s.nbr[NBR_SLOT(k, min(q + 2, nslots - 1))];
+        pj_next = ld_rec(&s.pos4[j_next]);
+        mj_next = s.vel4[j_next].w;
         double dx, dy, dz, W, g;
         const double r2 = pair_d2(pi, pj, dx, dy, dz);
-        if (MODE != LIST_EXACT && !pair_is_neighbour(r2, h2_i, pj)) continue;
+        if (MODE != LIST_EXACT && (j == k || !pair_is_neighbour(r2, h2_i, pj))) continue;
         if (MODE == LIST_VALIDATE) {
             if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
             cnt++;
@@ -515,7 +589,7 @@ k_density(Sorted s, b200sph_view v, double *rho_sorted, int n_targets, int *flag
 #else
         cubic_spline(r2, hinv_i, W, g);
 #endif
-        rho = fma(s.vel4[j].w, W, rho);
+        rho = fma(mj, W, rho);
     }
     if (MODE == LIST_VALIDATE) finish_validate(s, k, cnt, flags);
     rho_sorted[k] = rho;
@@ -868,12 +942,26 @@ k_correction(Sorted s, b200sph_view v, int n_targets, int *flags)
 #pragma unroll
             for (int b = 0; b < DIM; b++) A[a][b] = 0.0;
         int cnt = 0;
+        int j_next = 0, j_next2 = 0;
+        Rec4 pj_next = pi;
+        double vol_next = 0.0;
+        if (nslots > 0) {
+            j_next = s.nbr[NBR_SLOT(k, 0)];
+            j_next2 = s.nbr[NBR_SLOT(k, min(1, nslots - 1))];
+            pj_next = ld_rec(&s.pos4[j_next]);
+            vol_next = s.gas4[j_next].w;
+        }
         for (int q = 0; q < nslots; q++) {
-            const int j = s.nbr[NBR_SLOT(k, q)];
-            const Rec4 pj = ld_rec(&s.pos4[j]);
+            const int j = j_next;
+            const Rec4 pj = pj_next;
+            const double vol_j = vol_next;   /* m_j / rho_j */
+            j_next = j_next2;
+            j_next2 = s.nbr[NBR_SLOT(k, min(q + 2, nslots - 1))];
+            pj_next = ld_rec(&s.pos4[j_next]);
+            vol_next = s.gas4[j_next].w;
             double dr[3], W, g;
             const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
-            if (MODE != LIST_EXACT && !pair_is_neighbour(r2, h2_i, pj)) continue;
+            if (MODE != LIST_EXACT && (j == k || !pair_is_neighbour(r2, h2_i, pj))) continue;
             if (MODE == LIST_VALIDATE) {
                 if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
                 cnt++;
@@ -889,7 +977,7 @@ k_correction(Sorted s, b200sph_view v, int n_targets, int *flags)
 #else
             cubic_spline(r2, hinv, W, g);
 #endif
-            const double w = s.gas4[j].w * g;   /* (m_j/rho_j) * dW/dr / r */
+            const double w = vol_j * g;   /* (m_j/rho_j) * dW/dr / r */
             /* A is symmetric: accumulate the upper triangle only */
 #pragma unroll
             for (int a = 0; a < DIM; a++) {
@@ -955,11 +1043,11 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
     double acc[3] = {0.0, 0.0, 0.0}, drhodt = 0.0, dedt = 0.0, dhdt = 0.0, muijmax = 0.0;
     (void)dedt; (void)dhdt; (void)muijmax;
 #if SOLID
-    double edot[DIM][DIM], rdot[DIM][DIM];
+    double vgrad[DIM][DIM];
 #pragma unroll
     for (int a = 0; a < DIM; a++)
 #pragma unroll
-        for (int b = 0; b < DIM; b++) edot[a][b] = rdot[a][b] = 0.0;
+        for (int b = 0; b < DIM; b++) vgrad[a][b] = 0.0;
     double sig_i[DIM][DIM];
 #if TENSORIAL_CORRECTION
     double Ci[DIM][DIM];
@@ -1009,25 +1097,35 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
 #if ARTIFICIAL_STRESS
         const double w_ref_dist = M.mean_particle_distance;
 #endif
+        int j_next = s.nbr[NBR_SLOT(k, 0)];
+        int j_next2 = s.nbr[NBR_SLOT(k, min(1, nslots - 1))];
+        PairRecs nxt;
+        load_force_recs(s, j_next, nxt);
         for (int q = 0; q < nslots; q++) {
-            const int j = s.nbr[NBR_SLOT(k, q)];
-            const Rec4 pj = ld_rec(&s.pos4[j]);
+            const int j = j_next;
+            PairRecs cur = nxt;
+#if !B200_PREFETCH_TENSORS
+            load_tensor_recs(s, j, cur);
+#endif
+            j_next = j_next2;
+            j_next2 = s.nbr[NBR_SLOT(k, min(q + 2, nslots - 1))];
+            load_force_recs(s, j_next, nxt);   /* past the end this re-reads the last neighbour (harmless) */
+            const Rec4 &pj = cur.p;
             double dr[3], dv[3], W, g;
             const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
-            if (MODE != LIST_EXACT && !pair_is_neighbour(r2, h2_i, pj)) continue;
+            if (MODE != LIST_EXACT && (j == k || !pair_is_neighbour(r2, h2_i, pj))) continue;
             if (MODE == LIST_VALIDATE) {
                 if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
                 cnt++;
             }
             if (s.any_eos_ignore && mat_ignored(s.mat[j])) continue;
-            const Rec4 vj = ld_rec(&s.vel4[j]);
-            const Rec4 gj = ld_rec(&s.gas4[j]);
+            const Rec4 &vj = cur.v;
+            const Rec4 &gj = cur.g;
 #if SOLID
             double tj[4 * TEN_RECS];
 #pragma unroll
             for (int r = 0; r < TEN_RECS; r++) {
-                const Rec4 t = ld_rec(&s.ten[(size_t)j * TEN_RECS + r]);
-                tj[4 * r] = t.x; tj[4 * r + 1] = t.y; tj[4 * r + 2] = t.z; tj[4 * r + 3] = t.w;
+                tj[4 * r] = cur.t[r].x; tj[4 * r + 1] = cur.t[r].y; tj[4 * r + 2] = cur.t[r].z; tj[4 * r + 3] = cur.t[r].w;
             }
 #endif
             dv[0] = vi.x - vj.x; dv[1] = vi.y - vj.y; dv[2] = vi.z - vj.z;
@@ -1069,15 +1167,15 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
 #if SOLID
             /* strain rate and rotation rate, edot_ab = 1/2 (d_b v_a + d_a v_b) */
             {
+                /* accumulate the velocity gradient L_ab = sum w dv_a grad_b; edot = L + L^T and
+                 * rdot = L - L^T are formed once after the loop (9 accumulators instead of 18) */
                 const double w = -0.5 * mj * m_over_rho_i_unit;
 #pragma unroll
-                for (int a = 0; a < DIM; a++)
+                for (int a = 0; a < DIM; a++) {
+                    const double wa = w * dv[a];
 #pragma unroll
-                    for (int b = 0; b < DIM; b++) {
-                        const double t1 = dv[a] * gsym[b], t2 = dv[b] * gsym[a];
-                        edot[a][b] = fma(w, t1 + t2, edot[a][b]);
-                        rdot[a][b] = fma(w, t1 - t2, rdot[a][b]);
-                    }
+                    for (int b = 0; b < DIM; b++) vgrad[a][b] = fma(wa, gsym[b], vgrad[a][b]);
+                }
             }
 #endif
             double pij = 0.0;
@@ -1272,6 +1370,14 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
     {
         const double shear = M.shear, bulk = M.bulk, young = M.young;
         (void)bulk;
+        double edot[DIM][DIM], rdot[DIM][DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) {
+                edot[a][b] = vgrad[a][b] + vgrad[b][a];
+                rdot[a][b] = vgrad[a][b] - vgrad[b][a];
+            }
         double S[DIM][DIM];
 #pragma unroll
         for (int a = 0; a < DIM; a++)
@@ -1504,7 +1610,7 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     launches++;
     /* library plumbing (not counted in kernel_launches) */
     CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, h->cub_tmp_bytes, h->keys_in, s.keys, h->idx_in, s.perm, n, 0, h->sort_bits, st));
-    k_cell_start<<<blocks_for(n + 1, 256), 256, 0, st>>>(s.keys, n, h->d_domain, s.cell_start);
+    k_cell_start<<<blocks_for(n + 1, 256), 256, 0, st>>>(s.keys, n, h->d_domain, s.cell_start);   /* whole warps: no early exit inside */
     k_gather<<<blocks_for(n, 256), 256, 0, st>>>(v, s, h->d_domain);
     launches += 2;
     CU(cudaEventRecord(h->ev[1], st));
@@ -1541,8 +1647,9 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     launches++;
 #endif
     CU(cudaEventRecord(h->ev[5], st));
-    if (validated) k_forces<LIST_EXACT><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets, h->d_flags);
-    else k_forces<LIST_VALIDATE><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets, h->d_flags);
+    const int TF = h->forces_threads;
+    if (validated) k_forces<LIST_EXACT><<<blocks_for(n_targets, TF), TF, 0, st>>>(s, v, n_targets, h->d_flags);
+    else k_forces<LIST_VALIDATE><<<blocks_for(n_targets, TF), TF, 0, st>>>(s, v, n_targets, h->d_flags);
     k_list_stats<<<min(blocks_for(n, 256), 148 * 4), 256, 0, st>>>(s, h->d_flags);
     launches += 2;
     CU(cudaEventRecord(h->ev[6], st));
