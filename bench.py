@@ -206,19 +206,25 @@ def main() -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    from miluphcuda_b200 import multigpu
+
+    # Weak scaling: `--particles` per GPU.  ONE particle set of world x particles is generated (identically on
+    # every rank, the generators are deterministic) and cut along a Morton curve; every rank keeps its piece.
     workload = args.workload
-    sc = scenarios.make(workload, args.particles)
+    sc = scenarios.make(workload, args.particles * world)
     tmp = tempfile.TemporaryDirectory()
     cfg = state.write_material_files(sc, tmp.name)
-    eng = api.RhsEngine(workload, n_max=sc.n, device=local_rank, material_cfg=cfg)
-    arrays, meta = state.scenario_arrays(sc, eng.materials)
-    n = sc.n
+    mats = api.MaterialTables(workload, cfg)
+    full, meta = state.scenario_arrays(sc, mats)
+    arrays, n, capacity, _, dec = multigpu.scatter_scenario(full, sc.n, sc.dim, meta["max_num_flaws"], rank, world)
+    n_global = sc.n
+    del full
+    eng = api.RhsEngine(workload, n_max=capacity, device=local_rank, material_cfg=cfg)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
 
     dev = {k: torch.from_numpy(v).cuda() for k, v in arrays.items()}
-    view = api.make_view(dev, None, n, max_num_flaws=meta["max_num_flaws"], selfgravity=meta["selfgravity"],
-                         theta=meta["theta"], grav_const=eng.materials.grav_const)
+    drhs = multigpu.DistributedRhs(eng, dev, capacity, n, dec, meta, sc.switches())
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 512 MiB > 126 MB L2
 
     def barrier():
@@ -228,19 +234,22 @@ def main() -> None:
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        eng.rhs_eval(view)
+        drhs.eval()
     barrier()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
     stage_ms = {}
     launches = 0
     t_wall0 = time.time()
     for k in range(args.steps):
         flush.fill_(float(k))           # evict L2 between timed steps (not timed)
         ev[k][0].record(stream)
-        eng.rhs_eval(view)
+        drhs.exchange()                 # halo exchange (+ gravity sources) over NCCL; a no-op on one GPU
+        ev[k][2].record(stream)
+        drhs.compute()                  # b200sph_rhs_eval on owned + halo particles
         ev[k][1].record(stream)
         st = eng.stats()
         launches += st["kernel_launches"]
@@ -250,7 +259,8 @@ def main() -> None:
     barrier()
     t_wall = time.time() - t_wall0
     clocks = sampler.stop()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    dev_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
+    exch_ms = sum(a.elapsed_time(c) for a, _, c in ev)
     stats = eng.stats()
 
     # max over ranks of the device time for exactly K steps
@@ -263,27 +273,53 @@ def main() -> None:
     total_particles = float(cnt.item())
     value = total_particles * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end: host (pinned) buffers through the C-ABI, copies inside the timed region
+    # ---- end to end: host (pinned) buffers, copies inside the timed region.
+    # One GPU: the C-ABI's own host entry point (b200sph_rhs_eval_host).  Several GPUs: each rank uploads the
+    # state of its owned particles, runs exchange + evaluation, and reads every rate/state output back.
     e2e = None
     if not args.no_e2e:
         pinned = {k: torch.from_numpy(v).pin_memory() for k, v in arrays.items()}
-        hview = api.make_view(pinned, None, n, max_num_flaws=meta["max_num_flaws"], selfgravity=meta["selfgravity"],
-                              theta=meta["theta"], grav_const=eng.materials.grav_const)
+        if world == 1:
+            eng.set_owned(0)
+            hview = api.make_view(pinned, None, n, max_num_flaws=meta["max_num_flaws"], selfgravity=meta["selfgravity"],
+                                  theta=meta["theta"], grav_const=eng.materials.grav_const)
+
+            def e2e_step():
+                return eng.rhs_eval_host(hview)
+        else:
+            p_fields, rhs_fields = api.fields_for(sc.switches(), meta["selfgravity"])
+            outputs = [f for f in p_fields + rhs_fields if f in dev and f not in ("x", "y", "z", "m", "h0", "materialId", "flaws", "numFlaws")]
+            inputs = [f for f in dev if f in multigpu.HALO_STATE_FIELDS or f in ("flaws", "numFlaws", "numActiveFlaws", "pold")]
+
+            def e2e_step():
+                nb_in = nb_out = 0
+                for f in inputs:
+                    per = dev[f].numel() // capacity
+                    dev[f][: n * per].copy_(pinned[f][: n * per], non_blocking=True)
+                    nb_in += n * per * dev[f].element_size()
+                drhs.eval()
+                for f in outputs:
+                    per = dev[f].numel() // capacity
+                    pinned[f][: n * per].copy_(dev[f][: n * per], non_blocking=True)
+                    nb_out += n * per * dev[f].element_size()
+                torch.cuda.synchronize()
+                return nb_in, nb_out
         h2d = d2h = 0
         for _ in range(2):
-            h2d, d2h = eng.rhs_eval_host(hview)
+            h2d, d2h = e2e_step()
         barrier()
         e_steps = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(e_steps):
-            h2d, d2h = eng.rhs_eval_host(hview)
+            h2d, d2h = e2e_step()
         barrier()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": total_particles * e_steps / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
-               "timing": "host wall clock around b200sph_rhs_eval_host (sync on both sides), max over ranks"}
+               "timing": "host wall clock around the host-buffer call (sync on both sides), max over ranks",
+               "api": "b200sph_rhs_eval_host" if world == 1 else "pinned->device copies + DistributedRhs.eval + device->pinned copies"}
 
     if rank != 0:
         if world > 1:
@@ -294,7 +330,7 @@ def main() -> None:
     const = load_constants()
     peaks = measured_peaks()
     kind = const["workloads"][workload]
-    total_noi = float(dev["noi"].sum().item())
+    total_noi = float(dev["noi"][:n].sum().item())
     pairs = total_noi
     ms_forces = stage_ms.get("ms_forces", 0.0) / args.steps
     flops = kind["force_flop_per_pair"] * pairs + kind["force_flop_per_particle"] * n
@@ -318,10 +354,14 @@ def main() -> None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{workload} (synthetic, {n} particles per GPU)", "particles": int(total_particles),
+        "config": {"workload": f"{workload} (synthetic, {n_global} particles = {n_global // world} per GPU)", "particles": int(total_particles),
                    "mean_interactions": total_noi / n, "l2": "512 MiB buffer written between timed steps (untimed)",
                    "timing": "per-step CUDA events on the launching stream, summed over K steps, max over ranks",
-                   "multi_gpu": "replicas" if world > 1 else "single"},
+                   "multi_gpu": ("Morton-curve domain decomposition, %d-level halo exchange per evaluation (NCCL all_to_all)%s"
+                                 % (drhs.halo.levels, ", replicated gravity tree (NCCL all_gather of x,y,z,m)" if meta["selfgravity"] else ""))
+                   if world > 1 else "single",
+                   "rank0": {"owned": n, "halo": drhs.n_total - n, "halo_bytes_sent": drhs.halo.last.get("bytes_sent", 0),
+                             "exchange_ms_per_step": exch_ms / args.steps}},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "search_grid": {"cells": stats["n_cells"], "cell_size": stats["cell_size"], "max_interactions": stats["max_noi"]},

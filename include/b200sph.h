@@ -199,6 +199,29 @@ int b200sph_set_stream(b200sph_handle *h, void *cuda_stream);
 int b200sph_set_owned(b200sph_handle *h, int n_owned);
 /* Global bounding box (allreduced by the host) so every rank builds the same cells/tree. */
 int b200sph_set_global_domain(b200sph_handle *h, const double lo[3], const double hi[3]);
+/* Halo selection.  Every rank's domain is a set of axis-aligned boxes (the octree cells of its Morton key
+ * range); particle k must be copied to rank r when its distance to one of r's boxes b is below
+ * h[k] + extra[b] (extra[b] = largest smoothing length of the owner's particles inside box b for a
+ * two-level halo, 0 for a one-level halo).
+ * boxes: n_boxes x 6 doubles {lo_x, lo_y, lo_z, hi_x, hi_y, hi_z}, box_rank[b] in [0, 64) names the owner of
+ * box b, extra: n_boxes doubles (all three host or device memory); boxes of `my_rank` are skipped.
+ * x, y, z, h and mask_out are device pointers (y/z may be NULL below DIM 2/3); bit r of mask_out[k] is set
+ * when rank r needs particle k. */
+int b200sph_halo_mask(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
+                      const double *boxes, const int *box_rank, const double *extra, int n_boxes, int n_ranks, int my_rank,
+                      unsigned long long *mask_out);
+/* hmax_out[b] (device, n_boxes doubles) <- largest sml of the particles lying inside box b (0 if none). */
+int b200sph_halo_box_hmax(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
+                          const double *boxes, int n_boxes, double *hmax_out);
+/* Multi-GPU self-gravity with a replicated tree.  x,y,z,m (device pointers, n_sources doubles each; y/z may
+ * be NULL below DIM 2/3) describe the WHOLE particle set in a rank-independent order, normally the
+ * all-gather of every rank's owned particles; the caller's owned particles are the block
+ * [own_begin, own_begin + n_owned) of it and correspond to view.p[0, n_owned).  Every rank builds the same
+ * root cube and cells from the same data (the reference's geometry, src/tree.cu:1071-1086) and
+ * walks the tree for its own particles only (src/gravity.cu:382-499).  The pointers must stay valid during
+ * b200sph_rhs_eval; n_sources = 0 returns to single-GPU behaviour. */
+int b200sph_set_gravity_sources(b200sph_handle *h, const double *x, const double *y, const double *z, const double *m,
+                                int n_sources, int own_begin);
 
 #ifdef __cplusplus
 }

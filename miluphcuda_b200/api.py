@@ -121,6 +121,10 @@ _EXPORTS = {
     "b200sph_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200sph_set_owned": (C.c_int, [C.c_void_p, C.c_int]),
     "b200sph_set_global_domain": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "b200sph_halo_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b200sph_halo_box_hmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200sph_set_gravity_sources": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
 }
 _LIBS: dict = {}
 
@@ -320,6 +324,26 @@ class RhsEngine:
         a = (C.c_double * 3)(*[float(x) for x in lo])
         b = (C.c_double * 3)(*[float(x) for x in hi])
         self._check(self.lib.b200sph_set_global_domain(self.handle, a, b))
+
+    def halo_mask(self, x, y, z, h, n: int, boxes: np.ndarray, box_rank: np.ndarray, extra: np.ndarray, my_rank: int, mask_out) -> None:
+        """Bit r of mask_out[k] <- rank r needs particle k (device arrays; boxes/box_rank/extra are host numpy)."""
+        boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+        box_rank = np.ascontiguousarray(box_rank, dtype=np.int32)
+        extra = np.ascontiguousarray(extra, dtype=np.float64)
+        self._check(self.lib.b200sph_halo_mask(self.handle, _ptr_of(x), _ptr_of(y) or None, _ptr_of(z) or None, _ptr_of(h), n,
+                                               boxes.ctypes.data, box_rank.ctypes.data, extra.ctypes.data, len(box_rank),
+                                               int(box_rank.max()) + 1, my_rank, _ptr_of(mask_out)))
+
+    def halo_box_hmax(self, x, y, z, h, n: int, boxes: np.ndarray, hmax_out) -> None:
+        """hmax_out[b] (device) <- largest smoothing length inside box b."""
+        boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+        self._check(self.lib.b200sph_halo_box_hmax(self.handle, _ptr_of(x), _ptr_of(y) or None, _ptr_of(z) or None, _ptr_of(h), n,
+                                                   boxes.ctypes.data, len(boxes), _ptr_of(hmax_out)))
+
+    def set_gravity_sources(self, x, y, z, m, n_sources: int, own_begin: int) -> None:
+        """Multi-GPU gravity: device arrays of the global particle set (see include/b200sph.h)."""
+        self._check(self.lib.b200sph_set_gravity_sources(self.handle, _ptr_of(x) or None, _ptr_of(y) or None, _ptr_of(z) or None,
+                                                         _ptr_of(m) or None, n_sources, own_begin))
 
     def close(self) -> None:
         if self.handle:

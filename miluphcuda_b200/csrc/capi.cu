@@ -151,6 +151,7 @@ extern "C" int b200sph_destroy(b200sph_handle *h)
     cudaFree(h->keys_in); cudaFree(h->idx_in); cudaFree(h->rho_sorted); cudaFree(h->block_partials);
     cudaFree(h->block_counter); cudaFree(h->d_flags); cudaFree(h->d_domain); cudaFree(h->cub_tmp);
     cudaFree(h->stage);
+    cudaFree(h->halo_boxes);
     cudaFree(h->aneos_buf);
     for (int k = 0; k < 12; k++)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
@@ -291,6 +292,20 @@ extern "C" int b200sph_set_owned(b200sph_handle *h, int n_owned)
 {
     if (!h || n_owned < 0) return B200SPH_ERR_BAD_ARGUMENT;
     h->n_owned = n_owned;
+    return B200SPH_OK;
+}
+
+extern "C" int b200sph_set_gravity_sources(b200sph_handle *h, const double *x, const double *y, const double *z, const double *m,
+                                           int n_sources, int own_begin)
+{
+    if (!h) return B200SPH_ERR_BAD_ARGUMENT;
+    if (n_sources <= 0 || !x || !m) {
+        h->grav_src_n = 0;
+        return B200SPH_OK;
+    }
+    h->grav_src[0] = x; h->grav_src[1] = y; h->grav_src[2] = z; h->grav_src[3] = m;
+    h->grav_src_n = n_sources;
+    h->grav_own_begin = own_begin;
     return B200SPH_OK;
 }
 

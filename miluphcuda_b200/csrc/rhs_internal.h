@@ -95,6 +95,7 @@ struct Domain {
 
 struct Sorted {
     int n;
+    int n_owned;                /* caller indices >= n_owned are halo copies: no rates are produced for them */
     int any_eos_ignore;         /* a material with eos.type IGNORE exists: pair loops must look at mat[j] */
     int *perm;                  /* sorted slot -> caller index */
     int *keys;
@@ -127,9 +128,12 @@ struct b200sph_handle {
     double *rho_sorted;
     double *aneos_buf;          /* device copy of the tabulated-EOS payload */
     int n_owned;
+    const double *grav_src[4];  /* x, y, z, m of the global particle set (multi-GPU gravity), device pointers */
+    int grav_src_n, grav_own_begin;
     int forces_threads;         /* block size of k_forces: small blocks keep more warps resident at high register counts */
     int have_global_domain;
     double global_lo[3], global_hi[3];
+    void *halo_boxes;           /* device copy of the domain boxes (b200sph_halo_mask) */
     /* host-view staging (b200sph_rhs_eval_host) */
     void *stage;
     size_t stage_bytes;

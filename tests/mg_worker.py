@@ -1,0 +1,136 @@
+"""Worker of the multi-rank tests (spawned once per rank by torch.multiprocessing).
+
+mode "oracle": halo exchange on CPU tensors over gloo, then the CPU oracle on owned + halo particles --
+               checks that the decomposition hands every rank everything its particles interact with.
+mode "cuda"  : the same exchange, then libb200sph on a GPU (rank -> cuda:(rank % device_count)) with
+               b200sph_set_owned / b200sph_set_gravity_sources -- the N>1 product path.
+Each rank compares ITS owned particles with the single-domain oracle result computed from the same inputs.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+import traceback
+
+import numpy as np
+
+import common
+from miluphcuda_b200 import api, multigpu, scenarios, state
+
+FIELDS = ("ax", "ay", "az", "drhodt", "dedt", "dhdt", "dSdt", "dddt", "dalphadt", "rho", "p", "cs", "g_ax", "g_ay", "g_az")
+
+
+def _worker(rank: int, world: int, port: int, config: str, n: int, mode: str, backend: str, result_dir: str):
+    import torch
+    import torch.distributed as dist
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.set_num_threads(2)
+        use_cuda = mode == "cuda"
+        dev = torch.device("cpu")
+        if use_cuda:
+            dev = torch.device("cuda", rank % torch.cuda.device_count())
+            torch.cuda.set_device(dev)
+        kw = {"device_id": dev} if (use_cuda and backend == "nccl") else {}
+        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+
+        sc = scenarios.make(config, n, stirred=True)
+        sw = sc.switches()
+        with tempfile.TemporaryDirectory() as td:
+            cfg = state.write_material_files(sc, td)
+            mats = api.MaterialTables(config, cfg)
+            full, meta = state.scenario_arrays(sc, mats)
+            gravity = bool(meta["selfgravity"]) and use_cuda      # the oracle has no notion of foreign gravity sources
+            meta_run = dict(meta, selfgravity=gravity)
+
+            # single-domain answer
+            ref = {k: v.copy() for k, v in full.items()}
+            rc, off, _ = common.oracle_rhs(config, ref, mats, dict(meta_run, n=sc.n))
+            assert rc == 0, (rc, off)
+
+            local, n_owned, capacity, mine, dec = multigpu.scatter_scenario(full, sc.n, sc.dim, meta["max_num_flaws"], rank, world)
+            comm_dev = dev if backend == "nccl" else torch.device("cpu")
+            fields = {k: torch.from_numpy(v).to(comm_dev) for k, v in local.items()}
+            eng = api.RhsEngine(config, n_max=capacity, device=dev.index, material_cfg=cfg) if use_cuda else None
+            halo = multigpu.HaloExchange(fields, capacity, dec, levels=multigpu.halo_levels(sw), engine=eng)
+            n_total = halo.run(n_owned)
+            assert n_total > n_owned, "a rank without halo particles means the decomposition is not being exercised"
+
+            if use_cuda:
+                dfields = {k: v.to(dev) for k, v in fields.items()}
+                if gravity:
+                    gs = multigpu.GravitySources(sc.dim)
+                    gsrc = {k: v for k, v in (fields if backend == "nccl" else fields).items()}
+                    x, y, z, m, n_src, own_begin = gs.gather(gsrc, n_owned)
+                    to = lambda t: None if t is None else t.to(dev)
+                    x, y, z, m = to(x), to(y), to(z), to(m)
+                    eng.set_gravity_sources(x, y, z, m, n_src, own_begin)
+                view = api.make_view(dfields, None, n_total, max_num_flaws=meta["max_num_flaws"], selfgravity=gravity,
+                                     theta=meta["theta"], grav_const=eng.materials.grav_const)
+                eng.set_owned(n_owned)
+                eng.rhs_eval(view)
+                torch.cuda.synchronize()
+                stats = eng.stats()
+                assert stats["kernel_launches"] > 0
+                out = {k: v.cpu().numpy() for k, v in dfields.items()}
+                eng.close()
+            else:
+                out = {k: v.numpy() for k, v in fields.items()}
+                sub = {k: v.reshape(capacity, -1)[:n_total].reshape(-1).copy() for k, v in out.items()}
+                rc, off, _ = common.oracle_rhs(config, sub, mats, dict(meta_run, n=n_total))
+                assert rc == 0, (rc, off)
+                out = sub
+                capacity_rows = n_total
+            rows = capacity if use_cuda else n_total
+
+            bad = {}
+            got_noi = out["noi"].reshape(rows, -1)[:n_owned, 0]
+            if not np.array_equal(got_noi, ref["noi"][mine]):
+                bad["noi"] = int(np.abs(got_noi - ref["noi"][mine]).max())
+            tol = common.RTOL if use_cuda else 1e-11
+            for name in FIELDS:
+                if name not in out or name not in ref:
+                    continue
+                per = ref[name].size // sc.n
+                got = out[name].reshape(rows, per)[:n_owned]
+                want = ref[name].reshape(sc.n, per)[mine]
+                # scale of the whole field (not of this rank's piece) so a quiet piece is not judged against noise
+                scale = float(np.sqrt(np.mean(ref[name].astype(np.float64) ** 2)))
+                err = common.field_error(got, want, scale)
+                if not err <= tol:
+                    bad[name] = err
+            with open(os.path.join(result_dir, f"rank{rank}.txt"), "w") as fh:
+                fh.write("OK\n" if not bad else f"MISMATCH {bad}\n")
+                fh.write(f"n_owned={n_owned} n_halo={n_total - n_owned} sent={halo.last}\n")
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        with open(os.path.join(result_dir, f"rank{rank}.txt"), "w") as fh:
+            fh.write("EXCEPTION\n" + traceback.format_exc())
+        raise
+
+
+def run(config: str, n: int, world: int, mode: str, backend: str) -> list:
+    """Spawn `world` ranks; returns the per-rank result lines."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with tempfile.TemporaryDirectory() as rd:
+        try:
+            mp.spawn(_worker, args=(world, port, config, n, mode, backend, rd), nprocs=world, join=True)
+        finally:
+            lines = []
+            for r in range(world):
+                path = os.path.join(rd, f"rank{r}.txt")
+                lines.append(open(path).read() if os.path.exists(path) else "NO RESULT")
+    return lines
+
+
+if __name__ == "__main__":
+    cfg, n, world, mode, backend = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], sys.argv[5]
+    for r, text in enumerate(run(cfg, n, world, mode, backend)):
+        print(f"rank {r}: {text.strip()}")
