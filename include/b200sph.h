@@ -199,20 +199,38 @@ int b200sph_set_stream(b200sph_handle *h, void *cuda_stream);
 int b200sph_set_owned(b200sph_handle *h, int n_owned);
 /* Global bounding box (allreduced by the host) so every rank builds the same cells/tree. */
 int b200sph_set_global_domain(b200sph_handle *h, const double lo[3], const double hi[3]);
-/* Halo selection.  Every rank's domain is a set of axis-aligned boxes (the octree cells of its Morton key
- * range); particle k must be copied to rank r when its distance to one of r's boxes b is below
- * h[k] + extra[b] (extra[b] = largest smoothing length of the owner's particles inside box b for a
- * two-level halo, 0 for a one-level halo).
- * boxes: n_boxes x 6 doubles {lo_x, lo_y, lo_z, hi_x, hi_y, hi_z}, box_rank[b] in [0, 64) names the owner of
- * box b, extra: n_boxes doubles (all three host or device memory); boxes of `my_rank` are skipped.
- * x, y, z, h and mask_out are device pointers (y/z may be NULL below DIM 2/3); bit r of mask_out[k] is set
- * when rank r needs particle k. */
-int b200sph_halo_mask(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
-                      const double *boxes, const int *box_rank, const double *extra, int n_boxes, int n_ranks, int my_rank,
-                      unsigned long long *mask_out);
-/* hmax_out[b] (device, n_boxes doubles) <- largest sml of the particles lying inside box b (0 if none). */
+/* ---- halo exchange, device side (csrc/halo.cu).  Every rank's domain is a set of axis-aligned boxes (the
+ * octree cells of its Morton key range).  All calls are stream-ordered on the handle's stream and do not
+ * synchronise; pointers are device pointers unless stated otherwise. ---- */
+
+/* boxes: n_boxes x 6 doubles {lo_x, lo_y, lo_z, hi_x, hi_y, hi_z}, box_rank[b] = owner of box b, non-decreasing
+ * (HOST arrays); my_rank's boxes are the caller's own domain.  Call once per decomposition. */
+int b200sph_halo_set_domains(b200sph_handle *h, const double *boxes, const int *box_rank, int n_boxes, int n_ranks, int my_rank);
+/* hmax_out[j] <- largest sml among the n particles lying inside the caller's j-th box (0 if none);
+ * hmax_len >= number of own boxes, the tail is zeroed (so equal-sized pieces can be all-gathered). */
 int b200sph_halo_box_hmax(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
-                          const double *boxes, int n_boxes, double *hmax_out);
+                          double *hmax_out, int hmax_len);
+/* Particle k is needed by rank r when its distance to one of r's boxes b is below sml[k] + extra(b), where
+ * extra(b) = extra[r * extra_stride + j] for r's j-th box (the all-gather of every rank's hmax_out: two-level
+ * halo) or 0 when extra == NULL (one-level halo).  idx_out receives the indices of the particles to send,
+ * grouped by destination rank in rank order, ascending inside a group; counts_out[r] (n_ranks + 1 ints) the
+ * group sizes, counts_out[n_ranks] != 0 if idx_capacity was too small. */
+int b200sph_halo_select(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
+                        const double *extra, int extra_stride, int *idx_out, int idx_capacity, int *counts_out);
+/* One member of the reference's struct Particle taking part in the exchange: `per` values per particle;
+ * kind 0 = double, 1 = int32 (transported as double), 2 = int32 that is not transported but zeroed on the
+ * received rows (numFlaws, numActiveFlaws: the flaw lists of halo copies are never read). */
+typedef struct b200sph_halo_field {
+    void *data;
+    int per;
+    int kind;
+} b200sph_halo_field;
+/* doubles per packed row */
+int b200sph_halo_row_width(const b200sph_halo_field *fields, int n_fields);
+/* out[row * width + col] <- state of particle idx[row] (fields is a HOST array of n_fields descriptors) */
+int b200sph_halo_pack(b200sph_handle *h, const b200sph_halo_field *fields, int n_fields, const int *idx, int n_rows, double *out);
+/* particle rows [first_row, first_row + n_rows) <- in[row * width + col] */
+int b200sph_halo_unpack(b200sph_handle *h, const b200sph_halo_field *fields, int n_fields, const double *in, int n_rows, int first_row);
 /* Multi-GPU self-gravity with a replicated tree.  x,y,z,m (device pointers, n_sources doubles each; y/z may
  * be NULL below DIM 2/3) describe the WHOLE particle set in a rank-independent order, normally the
  * all-gather of every rank's owned particles; the caller's owned particles are the block

@@ -77,6 +77,10 @@ class Materials(C.Structure):
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(int(length),)).copy()
 
 
+class HaloField(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("per", C.c_int), ("kind", C.c_int)]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_int), ("n_cells", C.c_int), ("max_noi", C.c_int), ("total_noi", C.c_int64),
@@ -121,9 +125,13 @@ _EXPORTS = {
     "b200sph_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200sph_set_owned": (C.c_int, [C.c_void_p, C.c_int]),
     "b200sph_set_global_domain": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
-    "b200sph_halo_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "b200sph_halo_box_hmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200sph_halo_set_domains": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "b200sph_halo_box_hmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "b200sph_halo_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_int, C.c_void_p]),
+    "b200sph_halo_row_width": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200sph_halo_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200sph_halo_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "b200sph_set_gravity_sources": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
 }
 _LIBS: dict = {}
@@ -325,20 +333,41 @@ class RhsEngine:
         b = (C.c_double * 3)(*[float(x) for x in hi])
         self._check(self.lib.b200sph_set_global_domain(self.handle, a, b))
 
-    def halo_mask(self, x, y, z, h, n: int, boxes: np.ndarray, box_rank: np.ndarray, extra: np.ndarray, my_rank: int, mask_out) -> None:
-        """Bit r of mask_out[k] <- rank r needs particle k (device arrays; boxes/box_rank/extra are host numpy)."""
+    # ---- halo exchange, device side (csrc/halo.cu) ----
+    def halo_set_domains(self, boxes: np.ndarray, box_rank: np.ndarray, n_ranks: int, my_rank: int) -> None:
         boxes = np.ascontiguousarray(boxes, dtype=np.float64)
         box_rank = np.ascontiguousarray(box_rank, dtype=np.int32)
-        extra = np.ascontiguousarray(extra, dtype=np.float64)
-        self._check(self.lib.b200sph_halo_mask(self.handle, _ptr_of(x), _ptr_of(y) or None, _ptr_of(z) or None, _ptr_of(h), n,
-                                               boxes.ctypes.data, box_rank.ctypes.data, extra.ctypes.data, len(box_rank),
-                                               int(box_rank.max()) + 1, my_rank, _ptr_of(mask_out)))
+        self._check(self.lib.b200sph_halo_set_domains(self.handle, boxes.ctypes.data, box_rank.ctypes.data, len(box_rank), n_ranks, my_rank))
 
-    def halo_box_hmax(self, x, y, z, h, n: int, boxes: np.ndarray, hmax_out) -> None:
-        """hmax_out[b] (device) <- largest smoothing length inside box b."""
-        boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+    def halo_box_hmax(self, x, y, z, h, n: int, hmax_out) -> None:
         self._check(self.lib.b200sph_halo_box_hmax(self.handle, _ptr_of(x), _ptr_of(y) or None, _ptr_of(z) or None, _ptr_of(h), n,
-                                                   boxes.ctypes.data, len(boxes), _ptr_of(hmax_out)))
+                                                   _ptr_of(hmax_out), int(hmax_out.numel())))
+
+    def halo_select(self, x, y, z, h, n: int, extra, extra_stride: int, idx_out, counts_out) -> None:
+        self._check(self.lib.b200sph_halo_select(self.handle, _ptr_of(x), _ptr_of(y) or None, _ptr_of(z) or None, _ptr_of(h), n,
+                                                 _ptr_of(extra) or None, extra_stride, _ptr_of(idx_out), int(idx_out.numel()),
+                                                 _ptr_of(counts_out)))
+
+    @staticmethod
+    def halo_fields(fields: dict, names, capacity: int, zero_names=()):
+        """ctypes array of b200sph_halo_field for the named members of `fields` (flat tensors sized for `capacity`)."""
+        present = [n for n in names if n in fields] + [n for n in zero_names if n in fields]
+        arr = (HaloField * len(present))()
+        for k, name in enumerate(present):
+            t = fields[name]
+            arr[k].data = _ptr_of(t)
+            arr[k].per = t.numel() // capacity
+            arr[k].kind = 2 if name in zero_names else (1 if name in INT_FIELDS else 0)
+        return arr
+
+    def halo_row_width(self, desc) -> int:
+        return int(self.lib.b200sph_halo_row_width(desc, len(desc)))
+
+    def halo_pack(self, desc, idx, n_rows: int, out) -> None:
+        self._check(self.lib.b200sph_halo_pack(self.handle, desc, len(desc), _ptr_of(idx), n_rows, _ptr_of(out)))
+
+    def halo_unpack(self, desc, buf, n_rows: int, first_row: int) -> None:
+        self._check(self.lib.b200sph_halo_unpack(self.handle, desc, len(desc), _ptr_of(buf), n_rows, first_row))
 
     def set_gravity_sources(self, x, y, z, m, n_sources: int, own_begin: int) -> None:
         """Multi-GPU gravity: device arrays of the global particle set (see include/b200sph.h)."""

@@ -12,6 +12,7 @@ int upload_materials(b200sph_handle *h, const MatParams *host, int n, const Aneo
 int sort_temp_bytes(int n_max, int bits, size_t *bytes);
 int gravity_tree_create(b200sph_handle *h);
 void gravity_tree_destroy(b200sph_handle *h);
+void halo_state_destroy(b200sph_handle *h);
 
 /* ------------------------------------------------------------------ switch set identity */
 struct SwitchEntry {
@@ -151,7 +152,7 @@ extern "C" int b200sph_destroy(b200sph_handle *h)
     cudaFree(h->keys_in); cudaFree(h->idx_in); cudaFree(h->rho_sorted); cudaFree(h->block_partials);
     cudaFree(h->block_counter); cudaFree(h->d_flags); cudaFree(h->d_domain); cudaFree(h->cub_tmp);
     cudaFree(h->stage);
-    cudaFree(h->halo_boxes);
+    halo_state_destroy(h);
     cudaFree(h->aneos_buf);
     for (int k = 0; k < 12; k++)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);

@@ -7,4 +7,5 @@
  */
 #include "rhs_kernels.cu"
 #include "gravity.cu"
+#include "halo.cu"
 #include "capi.cu"

@@ -133,7 +133,7 @@ struct b200sph_handle {
     int forces_threads;         /* block size of k_forces: small blocks keep more warps resident at high register counts */
     int have_global_domain;
     double global_lo[3], global_hi[3];
-    void *halo_boxes;           /* device copy of the domain boxes (b200sph_halo_mask) */
+    void *halo;                 /* HaloState (halo.cu): domain boxes and selection scratch */
     /* host-view staging (b200sph_rhs_eval_host) */
     void *stage;
     size_t stage_bytes;

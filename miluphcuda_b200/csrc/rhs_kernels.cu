@@ -1737,121 +1737,6 @@ extern "C" int b200sph_damage_limit(b200sph_handle *h, const b200sph_view *view)
     return B200SPH_OK;
 }
 
-/* ------------------------------------------------------------------ halo selection (multi-GPU) */
-#define HALO_MAX_BOXES 1024
-struct HaloBoxes {
-    double lo[HALO_MAX_BOXES][3], hi[HALO_MAX_BOXES][3];
-    double extra[HALO_MAX_BOXES];
-    int rank[HALO_MAX_BOXES];
-};
-
-__global__ void __launch_bounds__(256)
-k_halo_mask(const double *x, const double *y, const double *z, const double *sml, int n, const HaloBoxes *boxes, int n_boxes,
-            int my_rank, unsigned long long *mask_out)
-{
-    extern __shared__ double sh_box[];   /* n_boxes x {lo[3], hi[3], extra} and the owner ids behind them */
-    double *bx = sh_box;
-    int *br = reinterpret_cast<int *>(sh_box + 7 * n_boxes);
-    for (int b = threadIdx.x; b < n_boxes; b += blockDim.x) {
-        const int r = boxes->rank[b];
-        for (int a = 0; a < 3; a++) {
-            bx[7 * b + a] = boxes->lo[b][a];
-            bx[7 * b + 3 + a] = boxes->hi[b][a];
-        }
-        bx[7 * b + 6] = boxes->extra[b];
-        br[b] = r;
-    }
-    __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const double p[3] = {x[k], (DIM > 1 && y) ? y[k] : 0.0, (DIM > 2 && z) ? z[k] : 0.0};
-    const double hk = sml[k];
-    unsigned long long mask = 0ull;
-    for (int b = 0; b < n_boxes; b++) {
-        const int r = br[b];
-        if (r == my_rank || ((mask >> r) & 1ull)) continue;
-        double d2 = 0.0;
-#pragma unroll
-        for (int a = 0; a < DIM; a++) {
-            const double g = fmax(fmax(bx[7 * b + a] - p[a], p[a] - bx[7 * b + 3 + a]), 0.0);
-            d2 = fma(g, g, d2);
-        }
-        const double reach = (hk + bx[7 * b + 6]) * (1.0 + 1e-9);
-        if (d2 < reach * reach) mask |= 1ull << r;
-    }
-    mask_out[k] = mask;
-}
-
-extern "C" int b200sph_halo_mask(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
-                                 const double *boxes, const int *box_rank, const double *extra, int n_boxes, int n_ranks, int my_rank,
-                                 unsigned long long *mask_out)
-{
-    if (!h || !x || !sml || !boxes || !box_rank || !extra || !mask_out || n < 0) return B200SPH_ERR_BAD_ARGUMENT;
-    if (n_boxes > HALO_MAX_BOXES || n_ranks > 64) {
-        snprintf(h->err, sizeof(h->err), "halo mask: %d boxes / %d ranks exceed the limits %d / 64", n_boxes, n_ranks, HALO_MAX_BOXES);
-        return B200SPH_ERR_UNSUPPORTED;
-    }
-    if (n == 0) return B200SPH_OK;
-    CU(cudaSetDevice(h->device));
-    if (!h->halo_boxes) CU(cudaMalloc(&h->halo_boxes, sizeof(HaloBoxes)));
-    static thread_local HaloBoxes hb;
-    double flat[6];
-    for (int b = 0; b < n_boxes; b++) {
-        CU(cudaMemcpy(flat, boxes + 6 * (size_t)b, sizeof(flat), cudaMemcpyDefault));
-        for (int a = 0; a < 3; a++) { hb.lo[b][a] = flat[a]; hb.hi[b][a] = flat[3 + a]; }
-    }
-    CU(cudaMemcpy(hb.rank, box_rank, sizeof(int) * n_boxes, cudaMemcpyDefault));
-    CU(cudaMemcpy(hb.extra, extra, sizeof(double) * n_boxes, cudaMemcpyDefault));
-    for (int b = 0; b < n_boxes; b++)
-        if (hb.rank[b] < 0 || hb.rank[b] >= n_ranks) return B200SPH_ERR_BAD_ARGUMENT;
-    CU(cudaMemcpyAsync(h->halo_boxes, &hb, sizeof(HaloBoxes), cudaMemcpyHostToDevice, h->stream));
-    const size_t smem = (size_t)n_boxes * (7 * sizeof(double) + sizeof(int));
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_halo_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_halo_mask<<<blocks_for(n, 256), 256, smem, h->stream>>>(x, y, z, sml, n, (const HaloBoxes *)h->halo_boxes, n_boxes, my_rank, mask_out);
-    CU(cudaStreamSynchronize(h->stream));   /* hb is reused by the next call */
-    CU(cudaGetLastError());
-    return B200SPH_OK;
-}
-
-__global__ void __launch_bounds__(256)
-k_halo_box_hmax(const double *x, const double *y, const double *z, const double *sml, int n, const HaloBoxes *boxes, int n_boxes,
-                unsigned long long *hmax_bits)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const double p[3] = {x[k], (DIM > 1 && y) ? y[k] : 0.0, (DIM > 2 && z) ? z[k] : 0.0};
-    for (int b = 0; b < n_boxes; b++) {
-        bool inside = true;
-#pragma unroll
-        for (int a = 0; a < DIM; a++) inside = inside && p[a] >= boxes->lo[b][a] && p[a] <= boxes->hi[b][a];
-        /* positive doubles order like their bit patterns */
-        if (inside) atomicMax(&hmax_bits[b], (unsigned long long)__double_as_longlong(sml[k]));
-    }
-}
-
-extern "C" int b200sph_halo_box_hmax(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
-                                     const double *boxes, int n_boxes, double *hmax_out)
-{
-    if (!h || !x || !sml || !boxes || !hmax_out || n < 0 || n_boxes <= 0) return B200SPH_ERR_BAD_ARGUMENT;
-    if (n_boxes > HALO_MAX_BOXES) return B200SPH_ERR_UNSUPPORTED;
-    CU(cudaSetDevice(h->device));
-    if (!h->halo_boxes) CU(cudaMalloc(&h->halo_boxes, sizeof(HaloBoxes)));
-    static thread_local HaloBoxes hb;
-    double flat[6];
-    for (int b = 0; b < n_boxes; b++) {
-        CU(cudaMemcpy(flat, boxes + 6 * (size_t)b, sizeof(flat), cudaMemcpyDefault));
-        for (int a = 0; a < 3; a++) { hb.lo[b][a] = flat[a]; hb.hi[b][a] = flat[3 + a]; }
-    }
-    CU(cudaMemcpyAsync(h->halo_boxes, &hb, sizeof(HaloBoxes), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemsetAsync(hmax_out, 0, sizeof(double) * n_boxes, h->stream));
-    if (n > 0)
-        k_halo_box_hmax<<<blocks_for(n, 256), 256, 0, h->stream>>>(x, y, z, sml, n, (const HaloBoxes *)h->halo_boxes, n_boxes,
-                                                                   reinterpret_cast<unsigned long long *>(hmax_out));
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaGetLastError());
-    return B200SPH_OK;
-}
-
 /* upload of the material tables into constant memory (used by capi.cu) */
 int upload_materials(b200sph_handle *h, const MatParams *host, int n, const AneosTables &tables)
 {

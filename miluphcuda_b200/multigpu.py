@@ -193,23 +193,84 @@ class HaloExchange:
         self.boxes, self.box_rank = dec.all_boxes()
         self.my_boxes = dec.boxes(self.rank)
         self.box_counts = [int((self.box_rank == r).sum()) for r in range(self.world)]
-        self.mask = None
+        self._desc = None
+        self._send = None
+        self._recv = None
         self.last = {}
 
     def _rows(self, name: str) -> torch.Tensor:
         return self.fields[name].view(self.capacity, -1)
 
+    # ------------------------------------------------------------------ GPU path: library kernels, two host reads
+    def _run_cuda(self, n_owned: int) -> int:
+        f = self.fields
+        dev = f["x"].device
+        eng = self.engine
+        if eng is None:
+            raise RuntimeError("halo exchange on GPU buffers needs the b200sph engine (no torch fallback on the product path)")
+        if self._desc is None:
+            eng.halo_set_domains(self.boxes, self.box_rank, self.world, self.rank)
+            self._desc = eng.halo_fields(f, self.exchange, self.capacity, HALO_ZERO_FIELDS)
+            self.width = eng.halo_row_width(self._desc)
+            self._nb_max = max(self.box_counts)
+            self._hmax_mine = torch.zeros(self._nb_max, dtype=torch.float64, device=dev)
+            self._hmax_all = torch.zeros(self.world * self._nb_max, dtype=torch.float64, device=dev)
+            self._idx = torch.empty(max(self.capacity, 2 * n_owned), dtype=torch.int32, device=dev)
+            self._counts = torch.zeros(self.world + 1, dtype=torch.int32, device=dev)
+            self._counts_host = torch.zeros(self.world + 1, dtype=torch.int32).pin_memory()
+            self._recv_counts = torch.zeros(self.world, dtype=torch.int32, device=dev)
+            self._recv_host = torch.zeros(self.world, dtype=torch.int32).pin_memory()
+        extra = None
+        if self.levels == 2:
+            eng.halo_box_hmax(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, self._hmax_mine)
+            dist.all_gather_into_tensor(self._hmax_all, self._hmax_mine, group=self.group)
+            extra = self._hmax_all
+        eng.halo_select(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, extra, self._nb_max, self._idx, self._counts)
+        dist.all_to_all_single(self._recv_counts, self._counts[: self.world], group=self.group)
+        self._counts_host.copy_(self._counts, non_blocking=True)
+        self._recv_host.copy_(self._recv_counts, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the only host wait: NCCL needs the split sizes
+        send_counts = [int(c) for c in self._counts_host[: self.world]]
+        recv_counts = [int(c) for c in self._recv_host]
+        if int(self._counts_host[self.world]) != 0:
+            raise RuntimeError(f"halo send list of {sum(send_counts)} entries does not fit {self._idx.numel()}")
+        n_send, n_recv = sum(send_counts), sum(recv_counts)
+        if n_owned + n_recv > self.capacity:
+            raise RuntimeError(f"halo of {n_recv} particles does not fit: capacity {self.capacity}, owned {n_owned}")
+        if self._send is None or self._send.numel() < n_send * self.width:
+            self._send = torch.empty(int(n_send * self.width * 1.2) + 64, dtype=torch.float64, device=dev)
+        if self._recv is None or self._recv.numel() < n_recv * self.width:
+            self._recv = torch.empty(int(n_recv * self.width * 1.2) + 64, dtype=torch.float64, device=dev)
+        send = self._send[: n_send * self.width].view(n_send, self.width)
+        recv = self._recv[: n_recv * self.width].view(n_recv, self.width)
+        eng.halo_pack(self._desc, self._idx, n_send, send)
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=self.group)
+        eng.halo_unpack(self._desc, recv, n_recv, n_owned)
+        self.last = dict(n_halo=n_recv, sent=n_send, bytes_sent=n_send * self.width * 8)
+        return n_owned + n_recv
+
+    # ------------------------------------------------------------------ CPU tensors (gloo tests): the same rule in torch ops
+    def _box_hmax(self, n_owned: int) -> np.ndarray:
+        """Largest smoothing length per box of every rank (host array aligned with self.boxes)."""
+        f = self.fields
+        nb_max = max(self.box_counts)
+        mine = torch.zeros(nb_max, dtype=torch.float64)
+        pos = torch.stack([f[a][:n_owned] for a in self.axes], dim=1)
+        h = f["h"][:n_owned]
+        for b in range(len(self.my_boxes)):
+            lo = torch.as_tensor(self.my_boxes[b, : self.dim])
+            hi = torch.as_tensor(self.my_boxes[b, 3: 3 + self.dim])
+            inside = ((pos >= lo) & (pos <= hi)).all(dim=1)
+            if bool(inside.any()):
+                mine[b] = h[inside].max()
+        flat = torch.empty(self.world * nb_max, dtype=torch.float64)
+        dist.all_gather_into_tensor(flat, mine, group=self.group)
+        table = flat.view(self.world, nb_max).numpy()
+        return np.concatenate([table[r, : self.box_counts[r]] for r in range(self.world)])
+
     def _needed_by(self, n_owned: int, extra: np.ndarray) -> torch.Tensor:
         """int64 mask per owned particle: bit r set <=> rank r needs a copy."""
         f = self.fields
-        dev = f["x"].device
-        if dev.type == "cuda":
-            if self.engine is None:
-                raise RuntimeError("halo selection on GPU buffers needs the b200sph engine (no torch fallback on the product path)")
-            if self.mask is None or self.mask.numel() < n_owned:
-                self.mask = torch.empty(self.capacity, dtype=torch.int64, device=dev)
-            self.engine.halo_mask(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, self.boxes, self.box_rank, extra, self.rank, self.mask)
-            return self.mask[:n_owned]
         pos = torch.stack([f[a][:n_owned] for a in self.axes], dim=1)
         h = f["h"][:n_owned]
         mask = torch.zeros(n_owned, dtype=torch.int64)
@@ -224,31 +285,6 @@ class HaloExchange:
             mask |= ((gap * gap).sum(dim=1) < reach * reach).to(torch.int64) << r
         return mask
 
-    def _box_hmax(self, n_owned: int) -> np.ndarray:
-        """Largest smoothing length per box of every rank (host array aligned with self.boxes)."""
-        f = self.fields
-        dev = f["x"].device
-        nb_max = max(self.box_counts)
-        mine = torch.zeros(nb_max, dtype=torch.float64, device=dev)
-        nb = len(self.my_boxes)
-        if dev.type == "cuda":
-            if self.engine is None:
-                raise RuntimeError("halo selection on GPU buffers needs the b200sph engine (no torch fallback on the product path)")
-            self.engine.halo_box_hmax(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, self.my_boxes, mine)
-        else:
-            pos = torch.stack([f[a][:n_owned] for a in self.axes], dim=1)
-            h = f["h"][:n_owned]
-            for b in range(nb):
-                lo = torch.as_tensor(self.my_boxes[b, : self.dim])
-                hi = torch.as_tensor(self.my_boxes[b, 3: 3 + self.dim])
-                inside = ((pos >= lo) & (pos <= hi)).all(dim=1)
-                if bool(inside.any()):
-                    mine[b] = h[inside].max()
-        flat = torch.empty(self.world * nb_max, dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(flat, mine, group=self.group)
-        table = flat.view(self.world, nb_max).cpu().numpy()
-        return np.concatenate([table[r, : self.box_counts[r]] for r in range(self.world)])
-
     def run(self, n_owned: int) -> int:
         """Fill rows [n_owned, n_owned + n_halo) with the copies this rank needs; returns n_owned + n_halo."""
         f = self.fields
@@ -256,12 +292,11 @@ class HaloExchange:
         if self.world == 1:
             self.last = dict(n_halo=0, sent=0, bytes_sent=0)
             return n_owned
+        if dev.type == "cuda":
+            return self._run_cuda(n_owned)
         # second halo level: a copy must also be complete around its own neighbours, which reach up to the
         # largest smoothing length found in the owner's box it borders (all-gathered per box)
-        if self.levels == 2:
-            extra = self._box_hmax(n_owned)
-        else:
-            extra = np.zeros(len(self.box_rank))
+        extra = self._box_hmax(n_owned) if self.levels == 2 else np.zeros(len(self.box_rank))
         mask = self._needed_by(n_owned, extra)
 
         send_idx, send_counts = [], []

@@ -54,6 +54,8 @@ def _worker(rank: int, world: int, port: int, config: str, n: int, mode: str, ba
             comm_dev = dev if backend == "nccl" else torch.device("cpu")
             fields = {k: torch.from_numpy(v).to(comm_dev) for k, v in local.items()}
             eng = api.RhsEngine(config, n_max=capacity, device=dev.index, material_cfg=cfg) if use_cuda else None
+            if eng is not None:
+                eng.set_stream(torch.cuda.current_stream().cuda_stream)   # library kernels ordered with torch / NCCL work
             halo = multigpu.HaloExchange(fields, capacity, dec, levels=multigpu.halo_levels(sw), engine=eng)
             n_total = halo.run(n_owned)
             assert n_total > n_owned, "a rank without halo particles means the decomposition is not being exercised"
