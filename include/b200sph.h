@@ -22,6 +22,8 @@
  *   2  B200SPH_ERR_BAD_ARGUMENT
  *   3  B200SPH_ERR_SWITCH_MISMATCH
  *   4  B200SPH_ERR_UNSUPPORTED            (switch / EOS outside the hot-path scope)
+ *   5  B200SPH_ERR_NONFINITE              (a particle coordinate or smoothing length is NaN/Inf; the reference
+ *                                          runs out of tree nodes in that situation, src/tree.cu:190-193)
  * `b200sph_last_error()` returns a human-readable description.
  */
 #ifndef B200SPH_H
@@ -41,6 +43,7 @@ extern "C" {
 #define B200SPH_ERR_BAD_ARGUMENT 2
 #define B200SPH_ERR_SWITCH_MISMATCH 3
 #define B200SPH_ERR_UNSUPPORTED 4
+#define B200SPH_ERR_NONFINITE 5
 #define B200SPH_ERR_CUDA (-1)
 
 /* Field-for-field mirror of the in-scope members of the reference's

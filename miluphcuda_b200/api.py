@@ -93,7 +93,7 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-ERRORS = {1: "TOO_MANY_INTERACTIONS", 2: "BAD_ARGUMENT", 3: "SWITCH_MISMATCH", 4: "UNSUPPORTED", -1: "CUDA"}
+ERRORS = {1: "TOO_MANY_INTERACTIONS", 2: "BAD_ARGUMENT", 3: "SWITCH_MISMATCH", 4: "UNSUPPORTED", 5: "NONFINITE", -1: "CUDA"}
 
 
 class B200SphError(RuntimeError):

@@ -117,17 +117,26 @@ static int halo_scratch(b200sph_handle *h, HaloState *st, int n)
 __global__ void __launch_bounds__(HALO_THREADS)
 h_box_hmax(const double *x, const double *y, const double *z, const double *sml, int n, const HaloDomains *dom, unsigned long long *hmax_bits)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const double p[3] = {x[k], (DIM > 1 && y) ? y[k] : 0.0, (DIM > 2 && z) ? z[k] : 0.0};
+    /* block-local maxima first: a million same-address global atomics would serialise in L2 */
+    __shared__ unsigned long long sh_max[HALO_MAX_BOXES];
     const int first = dom->my_first, count = dom->my_count;
-    for (int b = first; b < first + count; b++) {
-        bool inside = true;
-#pragma unroll
-        for (int a = 0; a < DIM; a++) inside = inside && p[a] >= dom->lo[b][a] && p[a] <= dom->hi[b][a];
+    for (int b = threadIdx.x; b < count; b += blockDim.x) sh_max[b] = 0ull;
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        const double p[3] = {x[k], (DIM > 1 && y) ? y[k] : 0.0, (DIM > 2 && z) ? z[k] : 0.0};
         /* positive doubles order like their bit patterns */
-        if (inside) atomicMax(&hmax_bits[b - first], (unsigned long long)__double_as_longlong(sml[k]));
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(sml[k]);
+        for (int b = 0; b < count; b++) {
+            bool inside = true;
+#pragma unroll
+            for (int a = 0; a < DIM; a++) inside = inside && p[a] >= dom->lo[first + b][a] && p[a] <= dom->hi[first + b][a];
+            if (inside && bits > sh_max[b]) atomicMax(&sh_max[b], bits);
+        }
     }
+    __syncthreads();
+    for (int b = threadIdx.x; b < count; b += blockDim.x)
+        if (sh_max[b] != 0ull) atomicMax(&hmax_bits[b], sh_max[b]);
 }
 
 extern "C" int b200sph_halo_box_hmax(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,

@@ -91,6 +91,7 @@ struct Domain {
     double h_max, h_mean;
     int nc[3];                  /* cells per axis */
     int n_cells;
+    int nonfinite;              /* bounding box or h statistics are NaN/Inf: the evaluation is void */
 };
 
 struct Sorted {

@@ -61,8 +61,8 @@ __device__ __forceinline__ double coord_of(const b200sph_particle_arrays &p, int
 }
 
 /* ------------------------------------------------------------------ k_prepare
- * values per block: min[3], max[3], sum h, max h, min h */
-#define PREP_VALUES 9
+ * values per block: min[3], max[3], sum h, max h, min h, number of non-finite coordinates */
+#define PREP_VALUES 10
 #define PREP_THREADS 256
 
 __global__ void __launch_bounds__(PREP_THREADS)
@@ -71,7 +71,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
 {
     const b200sph_particle_arrays &p = v.p;
     const b200sph_particle_arrays &pr = v.p_rhs;
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, hsum = 0.0, hmax = 0.0, hmin = 1e300;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, hsum = 0.0, hmax = 0.0, hmin = 1e300, bad = 0.0;
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
         const int matId = pr.materialId[i];
@@ -105,6 +105,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
             const double c = coord_of(p, i, a);
             lo[a] = fmin(lo[a], c);
             hi[a] = fmax(hi[a], c);
+            if (!isfinite(c)) bad += 1.0;   /* fmin/fmax drop NaNs silently */
         }
     }
 
@@ -120,6 +121,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
     vals[6] = warp_sum(hsum);
     vals[7] = warp_max(hmax);
     vals[8] = warp_min(hmin);
+    vals[9] = warp_sum(bad);
     if (lane == 0)
 #pragma unroll
         for (int k = 0; k < PREP_VALUES; k++) sh[warp][k] = vals[k];
@@ -133,6 +135,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
             sh[0][6] += sh[w][6];
             sh[0][7] = fmax(sh[0][7], sh[w][7]);
             sh[0][8] = fmin(sh[0][8], sh[w][8]);
+            sh[0][9] += sh[w][9];
         }
         for (int k = 0; k < PREP_VALUES; k++) partials[blockIdx.x * PREP_VALUES + k] = sh[0][k];
         __threadfence();
@@ -155,6 +158,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
         r[6] += q[6];
         r[7] = fmax(r[7], q[7]);
         r[8] = fmin(r[8], q[8]);
+        r[9] += q[9];
     }
     *counter = 0;
     Domain d;
@@ -178,6 +182,17 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
     for (int a = 0; a < 3; a++) d.root_centre[a] = 0.5 * (d.hi[a] + d.lo[a]);
     d.h_max = r[7];
     d.h_mean = r[6] / (double)v.n;
+    /* NaN/Inf coordinates or smoothing lengths: no grid can be built; report instead of indexing with garbage */
+    bool finite = isfinite(r[6]) && isfinite(r[7]) && r[8] > 0.0 && r[9] == 0.0;
+    for (int a = 0; a < DIM; a++) finite = finite && isfinite(d.lo[a]) && isfinite(d.hi[a]);
+    if (!finite) {
+        for (int a = 0; a < 3; a++) { d.lo[a] = 0.0; d.hi[a] = 0.0; d.root_centre[a] = 0.0; d.nc[a] = 1; }
+        d.root_radius = 0.0; d.cell = 1.0; d.cell_inv = 1.0; d.n_cells = 1; d.h_max = 0.0; d.h_mean = 0.0;
+        d.nonfinite = 1;
+        *dom = d;
+        return;
+    }
+    d.nonfinite = 0;
 #if VARIABLE_SML
     /* Cells as small as the smallest smoothing lengths: the bulk of a variable-resolution set sits at
      * the finest resolution, and a cell edge of 1.3 h_mean made those particles test ~1200 candidates
@@ -189,12 +204,14 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
 #endif
     if (!(cell > 0.0)) cell = 1.0;
     for (;;) {
-        double cells = 1.0;
+        /* counted in double: a far-flung particle makes the first guesses overflow an int */
+        double cells = 1.0, ncd[3];
         for (int a = 0; a < 3; a++) {
-            d.nc[a] = (a < DIM) ? (int)floor((d.hi[a] - d.lo[a]) / cell) + 1 : 1;
-            cells *= (double)d.nc[a];
+            ncd[a] = (a < DIM) ? floor((d.hi[a] - d.lo[a]) / cell) + 1.0 : 1.0;
+            cells *= ncd[a];
         }
         if (cells <= (double)max_cells) {
+            for (int a = 0; a < 3; a++) d.nc[a] = (int)ncd[a];
             d.n_cells = d.nc[0] * d.nc[1] * d.nc[2];
             break;
         }
@@ -382,6 +399,10 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags)
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_targets) return;
     const Domain &d = *dom;
+    if (d.nonfinite) {   /* void evaluation (reported by the host): do not scan the degenerate one-cell grid */
+        s.noi[k] = 0;
+        return;
+    }
     const Rec4 pi = ld_rec(&s.pos4[k]);
     const float4 si = s.srch[k];
     const float thr_i = search_threshold(pi.w, d);   /* srch.w is -1 for a deactivated target, which still collects neighbours */
@@ -1685,6 +1706,10 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     cudaEventElapsedTime(&S.ms_gravity, h->ev[6], h->ev[7]);
     S.ms_scatter = 0.0f;
 
+    if (h->h_domain.nonfinite) {
+        snprintf(h->err, sizeof(h->err), "non-finite particle coordinate or smoothing length (NaN/Inf) among the %d particles", v.n);
+        return B200SPH_ERR_NONFINITE;
+    }
     if (flags[0] != 0x7fffffff) {
         if (offender) *offender = flags[0];
         snprintf(h->err, sizeof(h->err), "particle %d has >= MAX_NUM_INTERACTIONS = %d interaction partners (reference: assert in src/tree.cu:917)",
