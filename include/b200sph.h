@@ -176,6 +176,19 @@ int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int *offender)
 int b200sph_rhs_eval_host(b200sph_handle *h, const b200sph_view *host_view, int *offender,
                           int64_t *h2d_bytes, int64_t *d2h_bytes);
 
+/* Options of the host-buffer call (default 0: every input is uploaded and every output member is
+ * read back on every call).
+ *   CACHE_IMMUTABLES  m, h0, materialId, numFlaws and flaws are uploaded on the first call only and
+ *                     reused while the same host arrays and particle count are passed -- the reference
+ *                     uploads them once per run as well (allocate_immutables, src/memory_handling.cu:111-122;
+ *                     copy_particles_immutables_device_to_device, src/memory_handling.cu:373-392).
+ *                     Calling b200sph_host_options() again drops the cached copy.
+ *   SKIP_SCRATCH      sigma, R, plastic_f and tensorialCorrectionMatrix (p_rhs scratch that no integrator
+ *                     or writer reads) are not copied back. */
+#define B200SPH_HOST_CACHE_IMMUTABLES 1
+#define B200SPH_HOST_SKIP_SCRATCH 2
+int b200sph_host_options(b200sph_handle *h, int options);
+
 /* Cold calls the reference makes outside rightHandSide():
  * calculatePressure by the writer and the PC integrators (src/io.cu:3039, src/predictor_corrector.cu:829),
  * damageLimit at output (src/rk2adaptive.cu:468), initializeSoundspeed at start (src/timeintegration.cu:206). */

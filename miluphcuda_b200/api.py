@@ -117,6 +117,7 @@ _EXPORTS = {
     "b200sph_set_materials": (C.c_int, [C.c_void_p, C.POINTER(Materials)]),
     "b200sph_rhs_eval": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(C.c_int)]),
     "b200sph_rhs_eval_host": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "b200sph_host_options": (C.c_int, [C.c_void_p, C.c_int]),
     "b200sph_pressure": (C.c_int, [C.c_void_p, C.POINTER(View)]),
     "b200sph_damage_limit": (C.c_int, [C.c_void_p, C.POINTER(View)]),
     "b200sph_init_soundspeed": (C.c_int, [C.c_void_p, C.POINTER(View)]),
@@ -301,6 +302,13 @@ class RhsEngine:
         rc = self.lib.b200sph_rhs_eval_host(self.handle, C.byref(view), C.byref(off), C.byref(h2d), C.byref(d2h))
         self._check(rc, off.value)
         return h2d.value, d2h.value
+
+    HOST_CACHE_IMMUTABLES = 1
+    HOST_SKIP_SCRATCH = 2
+
+    def host_options(self, options: int) -> None:
+        """B200SPH_HOST_* bits of the host-buffer call (include/b200sph.h); also drops cached immutables."""
+        self._check(self.lib.b200sph_host_options(self.handle, int(options)))
 
     def pressure(self, view: View) -> None:
         self._check(self.lib.b200sph_pressure(self.handle, C.byref(view)))

@@ -152,6 +152,9 @@ extern "C" int b200sph_destroy(b200sph_handle *h)
     cudaFree(h->keys_in); cudaFree(h->idx_in); cudaFree(h->rho_sorted); cudaFree(h->block_partials);
     cudaFree(h->block_counter); cudaFree(h->d_flags); cudaFree(h->d_domain); cudaFree(h->cub_tmp);
     cudaFree(h->stage);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int k = 0; k < 4; k++)
+        if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]);
     halo_state_destroy(h);
     cudaFree(h->aneos_buf);
     for (int k = 0; k < 12; k++)
@@ -365,6 +368,92 @@ static const FieldDesc k_fields[] = {
 static inline void **field_ptr(b200sph_particle_arrays *a, size_t off) { return (void **)((char *)a + off); }
 static inline void *const *field_ptr(const b200sph_particle_arrays *a, size_t off) { return (void *const *)((const char *)a + off); }
 
+/* roles of a member in the overlapped host-buffer call */
+static bool off_in(size_t off, const size_t *list, int n)
+{
+    for (int k = 0; k < n; k++)
+        if (list[k] == off) return true;
+    return false;
+}
+#define OFF(f) offsetof(b200sph_particle_arrays, f)
+/* never change during a run: the reference allocates/copies them once (allocate_immutables,
+ * src/memory_handling.cu:111-122; copy_particles_immutables_device_to_device, :373-392) */
+static const size_t k_immutable[] = {OFF(m), OFF(h0), OFF(materialId), OFF(numFlaws), OFF(flaws)};
+/* read by k_prepare / k_cell_keys / k_gather / k_neighbours / k_density: must land before the first kernel */
+static const size_t k_first_inputs[] = {OFF(x), OFF(y), OFF(z), OFF(vx), OFF(vy), OFF(vz), OFF(m), OFF(h), OFF(h0),
+                                        OFF(rho), OFF(e), OFF(materialId)};
+/* final once k_pointwise has run (k_correction / k_forces / gravity do not write them) */
+static const size_t k_early_outputs[] = {OFF(p), OFF(cs), OFF(S), OFF(alpha_jutzi_old), OFF(dalphadp), OFF(dalphadrho),
+                                         OFF(delpdele), OFF(delpdelrho), OFF(f), OFF(damage_total), OFF(damage_porjutzi),
+                                         OFF(h), OFF(e), OFF(sigma), OFF(R), OFF(plastic_f)};
+/* p_rhs scratch no caller reads (SURVEY 8b "outputs that callers read" does not list them) */
+static const size_t k_scratch_outputs[] = {OFF(sigma), OFF(R), OFF(plastic_f), OFF(tensorialCorrectionMatrix)};
+static const size_t k_velocity[] = {OFF(vx), OFF(vy), OFF(vz)};
+#undef OFF
+#define IN_LIST(off, list) off_in(off, list, (int)(sizeof(list) / sizeof(list[0])))
+
+struct HostCall {
+    const b200sph_view *hv;
+    b200sph_view dv;
+    size_t n, nf;
+    int64_t out_bytes;
+    cudaError_t err;
+};
+
+static size_t host_field_bytes(const FieldDesc &f, size_t n, size_t nf)
+{
+    const size_t per = f.per == -1 ? nf : (size_t)f.per;
+    return n * per * (f.is_int ? sizeof(int) : sizeof(double));
+}
+
+/* device->host copies of one output class on the copy stream: which = 0 early, 1 late */
+static void host_enqueue_outputs(b200sph_handle *h, HostCall *c, int which)
+{
+    const int nfields = (int)(sizeof(k_fields) / sizeof(k_fields[0]));
+    const bool skip_scratch = (h->host_options & B200SPH_HOST_SKIP_SCRATCH) != 0;
+    for (int k = 0; k < nfields && c->err == cudaSuccess; k++) {
+        const FieldDesc &f = k_fields[k];
+        const bool early = IN_LIST(f.offset, k_early_outputs);
+        if ((which == 0) != early) continue;
+        if (skip_scratch && IN_LIST(f.offset, k_scratch_outputs)) continue;
+        /* velocities come back unchanged unless k_prepare froze a particle (BoundaryConditionsBeforeRHS) */
+        if (IN_LIST(f.offset, k_velocity) && h->h_domain.n_frozen == 0) continue;
+        const size_t raw = host_field_bytes(f, c->n, c->nf);
+        void *hp = *field_ptr(&c->hv->p, f.offset);
+        void *hr = *field_ptr(&c->hv->p_rhs, f.offset);
+        if (hp && (f.out_p || (hr == hp && f.out_rhs))) {
+            c->err = cudaMemcpyAsync(hp, *field_ptr(&c->dv.p, f.offset), raw, cudaMemcpyDeviceToHost, h->copy_stream);
+            c->out_bytes += (int64_t)raw;
+        }
+        if (c->err == cudaSuccess && hr && hr != hp && f.out_rhs) {
+            c->err = cudaMemcpyAsync(hr, *field_ptr(&c->dv.p_rhs, f.offset), raw, cudaMemcpyDeviceToHost, h->copy_stream);
+            c->out_bytes += (int64_t)raw;
+        }
+    }
+}
+
+static void host_after_pointwise(b200sph_handle *h, void *ctx)
+{
+    HostCall *c = (HostCall *)ctx;
+    c->err = cudaEventRecord(h->ev_copy[2], h->stream);
+    if (c->err == cudaSuccess) c->err = cudaStreamWaitEvent(h->copy_stream, h->ev_copy[2], 0);
+    if (c->err == cudaSuccess) host_enqueue_outputs(h, c, 0);
+}
+
+extern "C" int b200sph_host_options(b200sph_handle *h, int options)
+{
+    if (!h) return B200SPH_ERR_BAD_ARGUMENT;
+    h->host_options = options;
+    h->host_imm_valid = 0;
+    return B200SPH_OK;
+}
+
+/* Three overlapped stages instead of copy-in / compute / copy-out:
+ *   compute stream : [first inputs H2D] prepare, sort, search, density | wait | pointwise | correction, forces, gravity
+ *   copy stream    :                    [late inputs H2D ............]          | [early outputs D2H ......] [late outputs D2H]
+ * "first inputs" are what the search reads (positions, h, velocities, rho, e); "early outputs" are the state
+ * k_pointwise finalises (p, c_s, S, porosity partials).  PCIe is full duplex but one call only has one
+ * direction busy at a time, so the gain is the kernels hidden behind the copies. */
 extern "C" int b200sph_rhs_eval_host(b200sph_handle *h, const b200sph_view *hv, int *offender, int64_t *h2d_bytes, int64_t *d2h_bytes)
 {
     if (!h || !hv || hv->n <= 0 || hv->n > h->n_max) return B200SPH_ERR_BAD_ARGUMENT;
@@ -372,10 +461,11 @@ extern "C" int b200sph_rhs_eval_host(b200sph_handle *h, const b200sph_view *hv, 
     const size_t n = (size_t)hv->n;
     const size_t nf = (size_t)(hv->max_num_flaws > 0 ? hv->max_num_flaws : 1);
     const int nfields = (int)(sizeof(k_fields) / sizeof(k_fields[0]));
-    auto bytes_of = [&](const FieldDesc &f) -> size_t {
-        const size_t per = f.per == -1 ? nf : (size_t)f.per;
-        return ((n * per * (f.is_int ? sizeof(int) : sizeof(double))) + 255) & ~(size_t)255;
-    };
+    if (!h->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 4; k++) CU(cudaEventCreateWithFlags(&h->ev_copy[k], cudaEventDisableTiming));
+    }
+    auto bytes_of = [&](const FieldDesc &f) -> size_t { return (host_field_bytes(f, n, nf) + 255) & ~(size_t)255; };
     /* device mirror: one slab, carved per present field (p first, then p_rhs when it has its own buffer) */
     size_t need = 0;
     for (int k = 0; k < nfields; k++) {
@@ -387,65 +477,90 @@ extern "C" int b200sph_rhs_eval_host(b200sph_handle *h, const b200sph_view *hv, 
         if (h->stage) cudaFree(h->stage);
         h->stage = nullptr;
         h->stage_bytes = 0;
+        h->host_imm_valid = 0;
         CU(cudaMalloc(&h->stage, need));
         h->stage_bytes = need;
     }
-    b200sph_view dv = *hv;
+    /* cached immutables stay valid only for the same host arrays and particle count */
+    const void *imm_key[6] = {hv->p.m, hv->p_rhs.h0, hv->p_rhs.materialId, hv->p.numFlaws ? (const void *)hv->p.numFlaws : (const void *)hv->p_rhs.numFlaws,
+                              hv->p_rhs.flaws, hv->p.x};
+    bool imm_cached = (h->host_options & B200SPH_HOST_CACHE_IMMUTABLES) && h->host_imm_valid && h->host_imm_n == hv->n;
+    for (int k = 0; k < 6 && imm_cached; k++) imm_cached = (imm_key[k] == h->host_imm_key[k]);
+
+    HostCall call;
+    call.hv = hv;
+    call.dv = *hv;
+    call.n = n;
+    call.nf = nf;
+    call.out_bytes = 0;
+    call.err = cudaSuccess;
+    b200sph_view &dv = call.dv;
     memset(&dv.p, 0, sizeof(dv.p));
     memset(&dv.p_rhs, 0, sizeof(dv.p_rhs));
-    char *cursor = (char *)h->stage;
-    int64_t in_bytes = 0, out_bytes = 0;
-    cudaStream_t st = h->stream;
-    for (int k = 0; k < nfields; k++) {
-        const FieldDesc &f = k_fields[k];
-        const size_t per = f.per == -1 ? nf : (size_t)f.per;
-        const size_t raw = n * per * (f.is_int ? sizeof(int) : sizeof(double));
-        void *hp = *field_ptr(&hv->p, f.offset);
-        void *hr = *field_ptr(&hv->p_rhs, f.offset);
-        void *dp = nullptr;
-        if (hp) {
-            dp = cursor;
-            cursor += bytes_of(f);
-            *field_ptr(&dv.p, f.offset) = dp;
-            if (f.in_p || (hr == hp && f.in_rhs)) {
-                CU(cudaMemcpyAsync(dp, hp, raw, cudaMemcpyHostToDevice, st));
-                in_bytes += (int64_t)raw;
-            }
+    int64_t in_bytes = 0;
+    cudaStream_t st = h->stream, cs = h->copy_stream;
+    /* pass 0 queues the first-stage inputs on the compute stream, pass 1 the late ones on the copy stream
+     * (behind the first stage, so the two do not share the host->device engine) */
+    for (int pass = 0; pass < 2; pass++) {
+        char *cursor = (char *)h->stage;
+        if (pass == 1) {
+            CU(cudaEventRecord(h->ev_copy[0], st));
+            CU(cudaStreamWaitEvent(cs, h->ev_copy[0], 0));
         }
-        if (hr) {
-            if (hr == hp) {
-                *field_ptr(&dv.p_rhs, f.offset) = dp;
-            } else {
-                void *dr = cursor;
+        for (int k = 0; k < nfields; k++) {
+            const FieldDesc &f = k_fields[k];
+            const size_t raw = host_field_bytes(f, n, nf);
+            const bool first = IN_LIST(f.offset, k_first_inputs);
+            const bool skip = imm_cached && IN_LIST(f.offset, k_immutable);
+            cudaStream_t q = first ? st : cs;
+            const bool mine = (first == (pass == 0));
+            void *hp = *field_ptr(&hv->p, f.offset);
+            void *hr = *field_ptr(&hv->p_rhs, f.offset);
+            void *dp = nullptr;
+            if (hp) {
+                dp = cursor;
                 cursor += bytes_of(f);
-                *field_ptr(&dv.p_rhs, f.offset) = dr;
-                if (f.in_rhs) {
-                    CU(cudaMemcpyAsync(dr, hr, raw, cudaMemcpyHostToDevice, st));
+                *field_ptr(&dv.p, f.offset) = dp;
+                if (mine && !skip && (f.in_p || (hr == hp && f.in_rhs))) {
+                    CU(cudaMemcpyAsync(dp, hp, raw, cudaMemcpyHostToDevice, q));
                     in_bytes += (int64_t)raw;
+                }
+            }
+            if (hr) {
+                if (hr == hp) {
+                    *field_ptr(&dv.p_rhs, f.offset) = dp;
+                } else {
+                    void *dr = cursor;
+                    cursor += bytes_of(f);
+                    *field_ptr(&dv.p_rhs, f.offset) = dr;
+                    if (mine && !skip && f.in_rhs) {
+                        CU(cudaMemcpyAsync(dr, hr, raw, cudaMemcpyHostToDevice, q));
+                        in_bytes += (int64_t)raw;
+                    }
                 }
             }
         }
     }
-    CU(cudaStreamSynchronize(st));
-    const int rc = b200sph_rhs_eval(h, &dv, offender);
-    if (rc != B200SPH_OK) return rc;
-    for (int k = 0; k < nfields; k++) {
-        const FieldDesc &f = k_fields[k];
-        const size_t per = f.per == -1 ? nf : (size_t)f.per;
-        const size_t raw = n * per * (f.is_int ? sizeof(int) : sizeof(double));
-        void *hp = *field_ptr(&hv->p, f.offset);
-        void *hr = *field_ptr(&hv->p_rhs, f.offset);
-        if (hp && (f.out_p || (hr == hp && f.out_rhs))) {
-            CU(cudaMemcpyAsync(hp, *field_ptr(&dv.p, f.offset), raw, cudaMemcpyDeviceToHost, st));
-            out_bytes += (int64_t)raw;
-        }
-        if (hr && hr != hp && f.out_rhs) {
-            CU(cudaMemcpyAsync(hr, *field_ptr(&dv.p_rhs, f.offset), raw, cudaMemcpyDeviceToHost, st));
-            out_bytes += (int64_t)raw;
-        }
+    CU(cudaEventRecord(h->ev_copy[1], cs));
+    h->hook_wait_before_pointwise = h->ev_copy[1];
+    h->hook_after_pointwise = host_after_pointwise;
+    h->hook_ctx = &call;
+    const int rc = b200sph_rhs_eval(h, &dv, offender);   /* returns with the compute stream drained */
+    h->hook_wait_before_pointwise = nullptr;
+    h->hook_after_pointwise = nullptr;
+    h->hook_ctx = nullptr;
+    if (rc == B200SPH_OK && call.err == cudaSuccess) host_enqueue_outputs(h, &call, 1);
+    const cudaError_t e_sync = cudaStreamSynchronize(cs);
+    if (rc != B200SPH_OK) {
+        h->host_imm_valid = 0;
+        return rc;
     }
-    CU(cudaStreamSynchronize(st));
+    CU(call.err);
+    CU(e_sync);
+    for (int k = 0; k < 6; k++) h->host_imm_key[k] = imm_key[k];
+    h->host_imm_n = hv->n;
+    h->host_imm_valid = 1;
     if (h2d_bytes) *h2d_bytes = in_bytes;
-    if (d2h_bytes) *d2h_bytes = out_bytes;
+    if (d2h_bytes) *d2h_bytes = call.out_bytes;
     return B200SPH_OK;
 }

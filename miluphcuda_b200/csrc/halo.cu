@@ -20,24 +20,7 @@
 #include <stdio.h>
 #include <string.h>
 
-#define HALO_MAX_BOXES 1024
-#define HALO_MAX_RANKS 64
 #define HALO_THREADS 256
-
-struct HaloDomains {
-    double lo[HALO_MAX_BOXES][3], hi[HALO_MAX_BOXES][3];
-    int rank[HALO_MAX_BOXES];       /* owner of box b */
-    int local[HALO_MAX_BOXES];      /* index of box b among its owner's boxes */
-    int n_boxes, n_ranks, my_rank, my_first, my_count;
-};
-
-struct HaloState {
-    HaloDomains host;
-    HaloDomains *dev;
-    unsigned long long *mask;       /* per particle: bit r = rank r needs it */
-    int *blk_counts;                /* [n_ranks][n_blocks] -> exclusive offsets after h_scan */
-    int mask_capacity, blk_capacity;
-};
 
 #define HCU(call)                                                                                    \
     do {                                                                                             \

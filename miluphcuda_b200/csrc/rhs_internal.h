@@ -92,6 +92,7 @@ struct Domain {
     int nc[3];                  /* cells per axis */
     int n_cells;
     int nonfinite;              /* bounding box or h statistics are NaN/Inf: the evaluation is void */
+    int n_frozen;               /* particles whose velocity k_prepare zeroed (deactivated / boundary material) */
 };
 
 struct Sorted {
@@ -106,6 +107,24 @@ struct Sorted {
     int *mat;
     Rec4 *ten;                  /* TEN_RECS records per particle (solid) */
     int *nbr, *noi;
+};
+
+/* multi-GPU: every rank's domain as a union of axis-aligned octree boxes (halo.cu) */
+#define HALO_MAX_BOXES 1024
+#define HALO_MAX_RANKS 64
+struct HaloDomains {
+    double lo[HALO_MAX_BOXES][3], hi[HALO_MAX_BOXES][3];
+    int rank[HALO_MAX_BOXES];       /* owner of box b */
+    int local[HALO_MAX_BOXES];      /* index of box b among its owner's boxes */
+    int n_boxes, n_ranks, my_rank, my_first, my_count;
+};
+
+struct HaloState {
+    HaloDomains host;
+    HaloDomains *dev;
+    unsigned long long *mask;       /* per particle: bit r = rank r needs it */
+    int *blk_counts;                /* [n_ranks][n_blocks] -> exclusive offsets after h_scan */
+    int mask_capacity, blk_capacity;
 };
 
 struct b200sph_handle {
@@ -138,6 +157,16 @@ struct b200sph_handle {
     /* host-view staging (b200sph_rhs_eval_host) */
     void *stage;
     size_t stage_bytes;
+    cudaStream_t copy_stream;   /* second DMA queue: late inputs / early outputs overlap the kernels */
+    cudaEvent_t ev_copy[4];     /* [0] first-stage inputs queued, [1] late inputs landed, [2] k_pointwise done */
+    int host_options;           /* B200SPH_HOST_* bits */
+    int host_imm_valid;         /* immutables of host_imm_key are resident in `stage` */
+    const void *host_imm_key[6];/* host pointers (m, h0, materialId, numFlaws, flaws, x) the cached copy came from */
+    int host_imm_n;
+    /* hooks of b200sph_rhs_eval used by the host-buffer entry point (NULL otherwise) */
+    cudaEvent_t hook_wait_before_pointwise;
+    void (*hook_after_pointwise)(struct b200sph_handle *, void *);
+    void *hook_ctx;
     b200sph_stats stats;
     /* gravity */
     struct GravityTree *tree;

@@ -61,8 +61,9 @@ __device__ __forceinline__ double coord_of(const b200sph_particle_arrays &p, int
 }
 
 /* ------------------------------------------------------------------ k_prepare
- * values per block: min[3], max[3], sum h, max h, min h, number of non-finite coordinates */
-#define PREP_VALUES 10
+ * values per block: min[3], max[3], sum h, max h, min h, number of non-finite coordinates,
+ * number of frozen particles (their velocities were zeroed) */
+#define PREP_VALUES 11
 #define PREP_THREADS 256
 
 __global__ void __launch_bounds__(PREP_THREADS)
@@ -71,7 +72,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
 {
     const b200sph_particle_arrays &p = v.p;
     const b200sph_particle_arrays &pr = v.p_rhs;
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, hsum = 0.0, hmax = 0.0, hmin = 1e300, bad = 0.0;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, hsum = 0.0, hmax = 0.0, hmin = 1e300, bad = 0.0, frozen = 0.0;
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
         const int matId = pr.materialId[i];
@@ -84,6 +85,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
 #if DIM > 2
             p.vz[i] = 0.0;
 #endif
+            frozen += 1.0;
         }
         if (matId >= 0 && matId != BOUNDARY_PARTICLE_ID) {
             const MatParams &M = c_mat[matId];
@@ -122,6 +124,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
     vals[7] = warp_max(hmax);
     vals[8] = warp_min(hmin);
     vals[9] = warp_sum(bad);
+    vals[10] = warp_sum(frozen);
     if (lane == 0)
 #pragma unroll
         for (int k = 0; k < PREP_VALUES; k++) sh[warp][k] = vals[k];
@@ -136,6 +139,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
             sh[0][7] = fmax(sh[0][7], sh[w][7]);
             sh[0][8] = fmin(sh[0][8], sh[w][8]);
             sh[0][9] += sh[w][9];
+            sh[0][10] += sh[w][10];
         }
         for (int k = 0; k < PREP_VALUES; k++) partials[blockIdx.x * PREP_VALUES + k] = sh[0][k];
         __threadfence();
@@ -143,22 +147,55 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
         is_last = (ticket == gridDim.x - 1);
     }
     __syncthreads();
-    if (!is_last || threadIdx.x != 0) return;
+    if (!is_last) return;
 
-    /* last block: combine and set up the search grid */
+    /* last block: all of its threads combine the per-block partials (one thread doing this alone cost
+     * 170 us for 592 blocks, profiles/r01_launches_sedov_v2.csv), then thread 0 sets up the search grid */
     __threadfence();
     double r[PREP_VALUES];
-    for (int k = 0; k < PREP_VALUES; k++) r[k] = partials[k];
-    for (unsigned int b = 1; b < gridDim.x; b++) {
-        const volatile double *q = partials + b * PREP_VALUES;
+#pragma unroll
+    for (int a = 0; a < 3; a++) { r[a] = 1e300; r[3 + a] = -1e300; }
+    r[6] = 0.0; r[7] = 0.0; r[8] = 1e300; r[9] = 0.0; r[10] = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        const double *q = partials + b * PREP_VALUES;
+#pragma unroll
         for (int a = 0; a < 3; a++) {
-            r[a] = fmin(r[a], q[a]);
-            r[3 + a] = fmax(r[3 + a], q[3 + a]);
+            r[a] = fmin(r[a], __ldcg(q + a));
+            r[3 + a] = fmax(r[3 + a], __ldcg(q + 3 + a));
         }
-        r[6] += q[6];
-        r[7] = fmax(r[7], q[7]);
-        r[8] = fmin(r[8], q[8]);
-        r[9] += q[9];
+        r[6] += __ldcg(q + 6);
+        r[7] = fmax(r[7], __ldcg(q + 7));
+        r[8] = fmin(r[8], __ldcg(q + 8));
+        r[9] += __ldcg(q + 9);
+        r[10] += __ldcg(q + 10);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        r[a] = warp_min(r[a]);
+        r[3 + a] = warp_max(r[3 + a]);
+    }
+    r[6] = warp_sum(r[6]);
+    r[7] = warp_max(r[7]);
+    r[8] = warp_min(r[8]);
+    r[9] = warp_sum(r[9]);
+    r[10] = warp_sum(r[10]);
+    __syncthreads();   /* sh[] is being reused */
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < PREP_VALUES; k++) sh[warp][k] = r[k];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (int k = 0; k < PREP_VALUES; k++) r[k] = sh[0][k];
+    for (int w = 1; w < PREP_THREADS / 32; w++) {
+        for (int a = 0; a < 3; a++) {
+            r[a] = fmin(r[a], sh[w][a]);
+            r[3 + a] = fmax(r[3 + a], sh[w][3 + a]);
+        }
+        r[6] += sh[w][6];
+        r[7] = fmax(r[7], sh[w][7]);
+        r[8] = fmin(r[8], sh[w][8]);
+        r[9] += sh[w][9];
+        r[10] += sh[w][10];
     }
     *counter = 0;
     Domain d;
@@ -182,6 +219,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
     for (int a = 0; a < 3; a++) d.root_centre[a] = 0.5 * (d.hi[a] + d.lo[a]);
     d.h_max = r[7];
     d.h_mean = r[6] / (double)v.n;
+    d.n_frozen = (int)r[10];
     /* NaN/Inf coordinates or smoothing lengths: no grid can be built; report instead of indexing with garbage */
     bool finite = isfinite(r[6]) && isfinite(r[7]) && r[8] > 0.0 && r[9] == 0.0;
     for (int a = 0; a < DIM; a++) finite = finite && isfinite(d.lo[a]) && isfinite(d.hi[a]);
@@ -393,8 +431,30 @@ __device__ __noinline__ int neighbours_exact(const Sorted &s, const Domain &d, i
     return cnt;
 }
 
+/* A halo copy needs its own neighbour list only when one of this rank's particles reads a neighbour SUM of
+ * it (kernel-sum density, tensorial correction matrix) -- that is, when it can be a neighbour of an owned
+ * particle at all: distance to this rank's boxes below its own h (criterion d < h_i^2 && d < h_j^2).  The
+ * outer halo level (copies that only complete those sums) and every copy of a one-level halo skip the search. */
+__device__ __forceinline__ bool halo_copy_needs_list(const Rec4 &pi, const HaloDomains *hd)
+{
+    const double reach = pi.w * (1.0 + 1e-9);
+    const double reach2 = reach * reach;
+    const double pos[3] = {pi.x, pi.y, pi.z};
+    const int first = hd->my_first, count = hd->my_count;
+    for (int b = 0; b < count; b++) {
+        double g2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+            const double g = fmax(fmax(hd->lo[first + b][a] - pos[a], pos[a] - hd->hi[first + b][a]), 0.0);
+            g2 = fma(g, g, g2);
+        }
+        if (g2 < reach2) return true;
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(128)
-k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags)
+k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloDomains *hd, int halo_sums)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_targets) return;
@@ -404,6 +464,10 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags)
         return;
     }
     const Rec4 pi = ld_rec(&s.pos4[k]);
+    if (hd != nullptr && s.perm[k] >= s.n_owned && (!halo_sums || !halo_copy_needs_list(pi, hd))) {
+        s.noi[k] = 0;
+        return;
+    }
     const float4 si = s.srch[k];
     const float thr_i = search_threshold(pi.w, d);   /* srch.w is -1 for a deactivated target, which still collects neighbours */
     const Stencil st = stencil_of(pi, d);
@@ -1619,7 +1683,7 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     const int T = 128;
 
     CU(cudaEventRecord(h->ev[0], st));
-    int init_flags[4] = {0x7fffffff, 0, 0, 0};
+    int init_flags[5] = {0x7fffffff, 0, 0, 0, 0};   /* [4]: gravity walk ran out of stack */
     CU(cudaMemcpyAsync(h->d_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
     {
         const int blocks = min(blocks_for(n, PREP_THREADS), 148 * 4);
@@ -1638,7 +1702,12 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     launches += 2;
     CU(cudaEventRecord(h->ev[1], st));
 
-    k_neighbours<<<blocks_for(n_targets, T), T, 0, st>>>(s, h->d_domain, n_targets, h->d_flags);
+    {
+        /* halo copies whose neighbour sums nobody reads skip the search (multi-GPU; boxes from b200sph_halo_set_domains) */
+        const HaloDomains *hd = (h->halo && s.n_owned < n) ? ((HaloState *)h->halo)->dev : nullptr;
+        const int halo_sums = (h->kernel_sum_density || TENSORIAL_CORRECTION) ? 1 : 0;
+        k_neighbours<<<blocks_for(n_targets, T), T, 0, st>>>(s, h->d_domain, n_targets, h->d_flags, hd, halo_sums);
+    }
     launches++;
     CU(cudaEventRecord(h->ev[2], st));
 
@@ -1660,8 +1729,12 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     }
     CU(cudaEventRecord(h->ev[3], st));
 
+    /* host-buffer entry point: the inputs only the pointwise chain and the pair loops read arrive on the
+     * copy stream while the search runs; the state k_pointwise finalises leaves while the pair loops run */
+    if (h->hook_wait_before_pointwise) CU(cudaStreamWaitEvent(st, h->hook_wait_before_pointwise, 0));
     k_pointwise<<<blocks_for(n, T), T, 0, st>>>(s, v, rho_sorted, use_rho_sorted);
     launches++;
+    if (h->hook_after_pointwise) h->hook_after_pointwise(h, h->hook_ctx);
     CU(cudaEventRecord(h->ev[4], st));
 #if TENSORIAL_CORRECTION
     if (validated) k_correction<LIST_EXACT><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets, h->d_flags);
@@ -1684,7 +1757,7 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     }
     CU(cudaEventRecord(h->ev[7], st));
 
-    int flags[4];
+    int flags[5];
     CU(cudaMemcpyAsync(flags, h->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&h->h_domain, h->d_domain, sizeof(Domain), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1709,6 +1782,10 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     if (h->h_domain.nonfinite) {
         snprintf(h->err, sizeof(h->err), "non-finite particle coordinate or smoothing length (NaN/Inf) among the %d particles", v.n);
         return B200SPH_ERR_NONFINITE;
+    }
+    if (flags[4] != 0) {
+        snprintf(h->err, sizeof(h->err), "gravity tree walk exceeded its traversal stack (tree deeper than the library supports)");
+        return B200SPH_ERR_UNSUPPORTED;
     }
     if (flags[0] != 0x7fffffff) {
         if (offender) *offender = flags[0];
