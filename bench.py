@@ -291,8 +291,12 @@ def main() -> None:
                 return eng.rhs_eval_host(hview)
         else:
             p_fields, rhs_fields = api.fields_for(sc.switches(), meta["selfgravity"])
-            outputs = [f for f in p_fields + rhs_fields if f in dev and f not in ("x", "y", "z", "m", "h0", "materialId", "flaws", "numFlaws")]
-            inputs = [f for f in dev if f in multigpu.HALO_STATE_FIELDS or f in ("flaws", "numFlaws", "numActiveFlaws", "pold")]
+            # same contract as the one-GPU host call with CACHE_IMMUTABLES|SKIP_SCRATCH: the integrated state goes up
+            # every step, immutables (m, h0, materialId, numFlaws, flaws) are resident, p_rhs scratch is not read back
+            immutable = ("m", "h0", "materialId", "flaws", "numFlaws")
+            scratch = ("sigma", "R", "plastic_f", "tensorialCorrectionMatrix")
+            outputs = [f for f in p_fields + rhs_fields if f in dev and f not in ("x", "y", "z", "vx", "vy", "vz") + immutable + scratch]
+            inputs = [f for f in dev if (f in multigpu.HALO_STATE_FIELDS or f in ("numActiveFlaws", "pold")) and f not in immutable]
 
             def e2e_step():
                 nb_in = nb_out = 0
@@ -324,7 +328,7 @@ def main() -> None:
                "timing": "host wall clock around the host-buffer call (sync on both sides), max over ranks",
                "api": ("b200sph_rhs_eval_host, options CACHE_IMMUTABLES|SKIP_SCRATCH: per-step inputs are the integrated state, "
                        "immutables (m, h0, materialId, flaws) uploaded once; copies overlapped with the kernels on a second stream")
-               if world == 1 else "pinned->device copies + DistributedRhs.eval + device->pinned copies"}
+               if world == 1 else "pinned->device copies of the integrated state + DistributedRhs.eval + device->pinned copies of every rate/state output (immutables resident, p_rhs scratch not read back)"}
 
     if rank != 0:
         if world > 1:

@@ -80,7 +80,7 @@ extern "C" int b200sph_create(b200sph_handle **out, int n_max, int device, uint6
     }
     const size_t n = (size_t)n_max;
     const size_t tiles = (n + NBR_TILE - 1) / NBR_TILE;
-    h->max_cells = (int)(2 * n + 4096 < (size_t)0x3fffffff ? 2 * n + 4096 : (size_t)0x3fffffff);
+    h->max_cells = (int)(8 * n + 4096 < (size_t)0x3fffffff ? 8 * n + 4096 : (size_t)0x3fffffff);
     h->sort_bits = 1;
     while ((1ll << h->sort_bits) < (long long)h->max_cells + 1) h->sort_bits++;
     if (sort_temp_bytes(n_max, h->sort_bits, &h->cub_tmp_bytes) != 0) h->cub_tmp_bytes = 0;
@@ -136,6 +136,9 @@ extern "C" int b200sph_create(b200sph_handle **out, int n_max, int device, uint6
         const char *env = getenv("B200SPH_FORCES_THREADS");
         const int t = env ? atoi(env) : 0;
         if (t == 32 || t == 64 || t == 96 || t == 128) h->forces_threads = t;
+        const char *pad = getenv("B200SPH_PAD_SMEM");
+        h->pad_smem = pad ? atoi(pad) : 0;
+        if (h->pad_smem < 0 || h->pad_smem > 48 * 1024) h->pad_smem = 0;
     }
     *out = h;
     return B200SPH_OK;

@@ -63,6 +63,9 @@ __device__ __forceinline__ double coord_of(const b200sph_particle_arrays &p, int
 /* ------------------------------------------------------------------ k_prepare
  * values per block: min[3], max[3], sum h, max h, min h, number of non-finite coordinates,
  * number of frozen particles (their velocities were zeroed) */
+#ifndef B200_CELL_DIV
+#define B200_CELL_DIV 2.0
+#endif
 #define PREP_VALUES 11
 #define PREP_THREADS 256
 
@@ -238,7 +241,8 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
      * (stencil_of) but live where cells are nearly empty.  Floored at h_mean/2 against outliers. */
     double cell = fmin(d.h_max, fmax(r[8], 0.5 * d.h_mean)) * 1.0001;
 #else
-    double cell = d.h_max * 1.0001;
+    /* fixed h: cells of half the smoothing length, 5x5(x5) stencil clipped to the sphere (k_neighbours) */
+    double cell = d.h_max * (1.0001 / B200_CELL_DIV);
 #endif
     if (!(cell > 0.0)) cell = 1.0;
     for (;;) {
@@ -453,6 +457,31 @@ __device__ __forceinline__ bool halo_copy_needs_list(const Rec4 &pi, const HaloD
     return false;
 }
 
+/* distance (>= 0) along one axis between coordinate p and the cells with index c; the outermost cells
+ * also hold the particles beyond the grid (cell_coord clamps), so they extend to infinity */
+__device__ __forceinline__ double row_gap(double p, double lo, double cell, int c, int nc, double slack)
+{
+    const double c_lo = fma((double)c, cell, lo);
+    const double below = (c > 0) ? c_lo - p : -1.0;
+    const double above = (c < nc - 1) ? p - (c_lo + cell) : -1.0;
+    return fmax(fmax(below, above) - slack, 0.0);
+}
+
+__device__ __forceinline__ bool search_hit(const float4 &si, float thr_i, const float4 c)
+{
+    const float dx = si.x - c.x;
+    float dd = dx * dx;
+#if DIM > 1
+    const float dy = si.y - c.y;
+    dd = fmaf(dy, dy, dd);
+#endif
+#if DIM > 2
+    const float dz = si.z - c.z;
+    dd = fmaf(dz, dz, dd);
+#endif
+    return dd < fminf(thr_i, c.w);
+}
+
 __global__ void __launch_bounds__(128)
 k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloDomains *hd, int halo_sums)
 {
@@ -472,32 +501,58 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloD
     const float thr_i = search_threshold(pi.w, d);   /* srch.w is -1 for a deactivated target, which still collects neighbours */
     const Stencil st = stencil_of(pi, d);
     /* The particle itself passes the filter (distance 0) and is stored like any survivor; the
-     * validating pair loop drops it.  That keeps the j != k comparison out of the candidate loop. */
+     * validating pair loop drops it.  That keeps the j != k comparison out of the candidate loop.
+     *
+     * Rows of x-adjacent cells are clipped to the sphere: a neighbour in row (y, z) is at least
+     * (g_y, g_z) away in y and z -- the gaps between the particle and the row's cells -- so it lies within
+     * w = sqrt(h_i^2 - g_y^2 - g_z^2) in x; rows with w^2 <= 0 are skipped.  With cells of half the largest h
+     * (k_prepare) this leaves ~120 candidates for ~47 hits instead of the 300 of a 3x3x3 block of h-sized cells. */
     int cnt = 0;
-    int *slot = s.nbr + NBR_SLOT(k, 0);
-    for (int z = st.z0; z <= st.z1; z++)
-        for (int y = st.y0; y <= st.y1; y++) {
-            const int row = d.nc[0] * (y + d.nc[1] * z);
-            const int jb = s.cell_start[row + st.x0], je = s.cell_start[row + st.x1 + 1];
-#pragma unroll 4
-            for (int j = jb; j < je; j++) {
-                const float4 c = __ldg(&s.srch[j]);
-                const float dx = si.x - c.x;
-                float dd = dx * dx;
-#if DIM > 1
-                const float dy = si.y - c.y;
-                dd = fmaf(dy, dy, dd);
-#endif
+    int *const base = s.nbr + NBR_SLOT(k, 0);
+    const double reach2 = __dmul_rn(pi.w, pi.w) * (1.0 + 1e-9);
+    const double slack = 1e-9 * d.cell;
+    for (int z = st.z0; z <= st.z1; z++) {
 #if DIM > 2
-                const float dz = si.z - c.z;
-                dd = fmaf(dz, dz, dd);
+        const double gz = row_gap(pi.z, d.lo[2], d.cell, z, d.nc[2], slack);
+        const double rem_z = reach2 - gz * gz;
+        if (rem_z <= 0.0) continue;
+#else
+        const double rem_z = reach2;
 #endif
-                const bool hit = dd < fminf(thr_i, c.w);
-                if (hit && cnt < MAX_NUM_INTERACTIONS) *slot = j;   /* predicated store, no divergent branch */
-                slot += hit ? NBR_TILE : 0;
-                cnt += hit ? 1 : 0;
+        for (int y = st.y0; y <= st.y1; y++) {
+#if DIM > 1
+            const double gy = row_gap(pi.y, d.lo[1], d.cell, y, d.nc[1], slack);
+            const double rem = rem_z - gy * gy;
+            if (rem <= 0.0) continue;
+#else
+            const double rem = rem_z;
+#endif
+            /* FP32 square root rounded up, then widened: never narrower than the exact half-width */
+            const double w = (double)__fsqrt_ru(__double2float_ru(rem)) * (1.0 + 1e-6) + slack;
+            const int xa = max(st.x0, cell_coord(pi.x - w, d.lo[0], d.cell_inv, d.nc[0]));
+            const int xb = min(st.x1, cell_coord(pi.x + w, d.lo[0], d.cell_inv, d.nc[0]));
+            const int row = d.nc[0] * (y + d.nc[1] * z);
+            const int jb = s.cell_start[row + xa], je = s.cell_start[row + xb + 1];
+            if (cnt + (je - jb) <= MAX_NUM_INTERACTIONS) {
+                /* the whole row fits: no overflow check per candidate */
+                int *slot = base + cnt * NBR_TILE;
+#pragma unroll 4
+                for (int j = jb; j < je; j++) {
+                    const bool hit = search_hit(si, thr_i, __ldg(&s.srch[j]));
+                    if (hit) *slot = j;   /* predicated store, no divergent branch */
+                    slot += hit ? NBR_TILE : 0;
+                    cnt += hit ? 1 : 0;
+                }
+            } else {
+                for (int j = jb; j < je; j++) {
+                    if (search_hit(si, thr_i, __ldg(&s.srch[j]))) {
+                        if (cnt < MAX_NUM_INTERACTIONS) base[cnt * NBR_TILE] = j;
+                        cnt++;
+                    }
+                }
             }
         }
+    }
     if (cnt > MAX_NUM_INTERACTIONS) {
         /* more survivors than list slots: decide with the exact test (the reference asserts on the exact count) */
         cnt = neighbours_exact(s, d, k, pi, st);
@@ -1273,10 +1328,14 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
                 if (vr < 0.0) {
                     const double csbar = 0.5 * (gi.y + gj.y);
                     const double smooth = 0.5 * (pi.w + pj.w);
-                    const double mu = smooth * vr / (r2 + smooth * smooth * 1e-2);
-                    muijmax = fmax(muijmax, mu);
+                    /* mu = h vr / (r^2 + 0.01 h^2) and Pi = (beta mu - alpha c) mu / rho_bar with ONE division:
+                     * 1/(A B) gives 1/A = B/(A B) and 1/B = A/(A B) (rounding-level difference to two divisions) */
+                    const double den = fma(smooth * smooth, 1e-2, r2);
                     const double rhobar = 0.5 * (gi.z + gj.z);
-                    pij = (av_beta * mu - av_alpha * csbar) * mu / rhobar;
+                    const double inv = 1.0 / (den * rhobar);
+                    const double mu = smooth * vr * (inv * rhobar);
+                    muijmax = fmax(muijmax, mu);
+                    pij = (av_beta * mu - av_alpha * csbar) * mu * (inv * den);
                 }
             }
 #endif
@@ -1720,9 +1779,9 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     int validated = 0;
     if (use_rho_sorted) {
 #if INTEGRATE_DENSITY
-        k_density<LIST_CHECK><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, rho_sorted, n_targets, h->d_flags);
+        k_density<LIST_CHECK><<<blocks_for(n_targets, T), T, h->pad_smem, st>>>(s, v, rho_sorted, n_targets, h->d_flags);
 #else
-        k_density<LIST_VALIDATE><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, rho_sorted, n_targets, h->d_flags);
+        k_density<LIST_VALIDATE><<<blocks_for(n_targets, T), T, h->pad_smem, st>>>(s, v, rho_sorted, n_targets, h->d_flags);
         validated = 1;
 #endif
         launches++;
@@ -1744,8 +1803,8 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
 #endif
     CU(cudaEventRecord(h->ev[5], st));
     const int TF = h->forces_threads;
-    if (validated) k_forces<LIST_EXACT><<<blocks_for(n_targets, TF), TF, 0, st>>>(s, v, n_targets, h->d_flags);
-    else k_forces<LIST_VALIDATE><<<blocks_for(n_targets, TF), TF, 0, st>>>(s, v, n_targets, h->d_flags);
+    if (validated) k_forces<LIST_EXACT><<<blocks_for(n_targets, TF), TF, h->pad_smem, st>>>(s, v, n_targets, h->d_flags);
+    else k_forces<LIST_VALIDATE><<<blocks_for(n_targets, TF), TF, h->pad_smem, st>>>(s, v, n_targets, h->d_flags);
     k_list_stats<<<min(blocks_for(n, 256), 148 * 4), 256, 0, st>>>(s, h->d_flags);
     launches += 2;
     CU(cudaEventRecord(h->ev[6], st));

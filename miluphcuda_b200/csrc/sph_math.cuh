@@ -62,10 +62,22 @@ __device__ __forceinline__ double kernel_norm(double hinv)
 #endif
 }
 
+/* Measured on a B200 (gpurun_out v1/q2, round 1): pinning the reciprocal square root in a register cuts the
+ * solid pair loops by 30 % (impact k_forces 1.70 -> 1.20 ms: the FP64 pipe was the busiest unit there), but
+ * slows the hydro loops by 15 % (sedov k_forces 0.364 -> 0.420 ms: they are bound by L1TEX wavefronts and the
+ * leaner code raises occupancy and with it the L1 miss rate).  Hence per switch set. */
+#ifndef B200_RSQRT_OPAQUE
+#define B200_RSQRT_OPAQUE SOLID
+#endif
 __device__ __forceinline__ void cubic_spline(double r2, double hinv, double &W, double &g)
 {
     const double f = kernel_norm(hinv);
-    const double rinv = rsqrt(r2);
+    double rinv = rsqrt(r2);
+    /* opaque to the optimiser: nvcc otherwise re-evaluates the reciprocal square root (MUFU + 5 FP64
+     * instructions + slow-path check) in each branch below instead of keeping it in a register */
+#if B200_RSQRT_OPAQUE
+    asm volatile("" : "+d"(rinv));
+#endif
     const double r = r2 * rinv;
     const double q = r * hinv;
     if (q > 1.0) {
