@@ -397,7 +397,52 @@ def _giant_cfg(sml: float) -> str:
     )
 
 
-def giant(n_target: int = 59899, solid: bool = False, seed: int = 7) -> Scenario:
+# ANEOS variant of the giant collision (north_star: "the EOS including tabulated ANEOS").
+# The real M-ANEOS tables are not shipped with the reference, so a table in the reference's format
+# (src/aneos.cu:119-181: three header lines, then n_rho x n_e rows "rho e p T cs entropy phase", rho in the
+# outer loop) is synthesised from a Tillotson-like closed form.  The grid is deliberately narrower than the
+# particle states so that every branch of the lookup runs: rho below / above the table (edge-cell
+# extrapolation), e below the table (clamped) and e above it (ideal-gas fallback, src/pressure.cu / aneos.cu).
+_ANEOS_PARAMS = {
+    "iron": dict(rho0=7800.0, A=1.28e11, B=1.05e11, E0=9.5e6, a=0.5, b=1.5, bulk_cs=4050.0),
+    "granite": dict(rho0=2680.0, A=1.8e10, B=1.8e10, E0=1.6e7, a=0.5, b=1.3, bulk_cs=2590.0),
+}
+ANEOS_N_RHO, ANEOS_N_E = 40, 36
+
+
+def aneos_table_text(name: str) -> str:
+    q = _ANEOS_PARAMS[name]
+    rho = q["rho0"] * np.geomspace(0.62, 1.10, ANEOS_N_RHO)
+    e = np.geomspace(2.0e4, 1.0e7, ANEOS_N_E)
+    lines = [f"# synthetic ANEOS-format table for {name} (miluphcuda_b200/scenarios.py)",
+             f"# n_rho = {ANEOS_N_RHO}, n_e = {ANEOS_N_E}", "# rho e p T cs entropy phase"]
+    for r in rho:
+        eta = r / q["rho0"]
+        mu = eta - 1.0
+        for en in e:
+            om = en / (q["E0"] * eta * eta) + 1.0
+            pres = (q["a"] + q["b"] / om) * r * en + q["A"] * mu + q["B"] * mu * mu
+            cs2 = q["a"] * en + q["b"] * en / (om * om) * (3.0 * om - 2.0) + (q["A"] + 2.0 * q["B"] * mu) / r
+            cs = np.sqrt(max(cs2, (0.05 * q["bulk_cs"]) ** 2))
+            temp = 300.0 + en / 800.0
+            lines.append(f"{r:.16e} {en:.16e} {pres:.16e} {temp:.6e} {cs:.16e} {1000.0 + 0.1 * temp:.6e} 1")
+    return "\n".join(lines) + "\n"
+
+
+def _giant_aneos_cfg(sml: float) -> str:
+    def mat(i, name, key, floor):
+        q = _ANEOS_PARAMS[key]
+        return (
+            f"  {{\n    ID = {i}\n    name = \"{name}\";\n    sml = {sml:.17e}\n    interactions = 30\n    {_AV}\n"
+            f"    density_floor = {floor}\n    eos = {{\n      type = 7\n      table_path = \"{key}.aneos.table\"\n"
+            f"      n_rho = {ANEOS_N_RHO}\n      n_e = {ANEOS_N_E}\n      aneos_rho_0 = {q['rho0']}\n"
+            f"      aneos_bulk_cs = {q['bulk_cs']}\n      aneos_gamma = 1.4\n      rho_limit = 0.9\n    }};\n  }}"
+        )
+
+    return "materials = (\n" + mat(0, "Iron", "iron", "100.") + ",\n" + mat(1, "Granite", "granite", "10.") + "\n);\n"
+
+
+def giant(n_target: int = 59899, solid: bool = False, seed: int = 7, aneos: bool = False) -> Scenario:
     """Two differentiated bodies (iron core id 0, granite mantle id 1) about to collide.
 
     Geometry and kinematics from the shipped run (target R = 1.70e6 m, core
@@ -437,6 +482,9 @@ def giant(n_target: int = 59899, solid: bool = False, seed: int = 7) -> Scenario
     n = x.shape[0]
     cfg = _giant_cfg(sml)
     inc = {"iron.till.cfg": _IRON_TILL, "granite.till.cfg": _GRANITE_TILL}
+    if aneos:
+        cfg = _giant_aneos_cfg(sml)
+        inc = {"iron.aneos.table": aneos_table_text("iron"), "granite.aneos.table": aneos_table_text("granite")}
     if not solid:
         return Scenario("giant_hydro", 3, x, v, m, cfg, rho=rho, e=e, mat=mat, includes=inc, selfgravity=True)
     rng = np.random.default_rng(seed)
@@ -519,6 +567,8 @@ def make(config: str, n: int | None = None, stirred: bool = False) -> Scenario:
         return impact() if n is None else impact(n_target=n)
     if config == "giant_hydro":
         return giant() if n is None else giant(n_target=n)
+    if config == "giant_aneos":   # the giant_hydro switch set (same library) with tabulated-EOS materials
+        return giant(aneos=True) if n is None else giant(n_target=n, aneos=True)
     if config == "giant_solid":
         return giant(solid=True) if n is None else giant(n_target=n, solid=True)
     raise ValueError(f"unknown config {config!r}")

@@ -33,7 +33,8 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from miluphcuda_b200 import scenarios  # noqa: E402
 
-GOLDEN_N = {"shocktube": None, "sedov": 2500, "rings": 2500, "impact": 2500, "giant_hydro": 2500, "giant_solid": 2500}
+GOLDEN_N = {"shocktube": None, "sedov": 2500, "rings": 2500, "impact": 2500, "giant_hydro": 2500, "giant_solid": 2500,
+            "giant_aneos": 2500}   # giant_aneos: the giant_hydro build with tabulated-EOS materials
 
 
 def read_dump(path: str) -> dict:

@@ -16,7 +16,10 @@ from miluphcuda_b200 import api, scenarios  # noqa: E402
 
 GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
 CONFIGS = scenarios.CONFIG_NAMES
-GOLDEN_CASES = [f"{c}{s}" for c in CONFIGS for s in ("", "_stirred")]
+# scenario variants that run on another config's switch set (library): the giant collision with tabulated-EOS
+# (ANEOS-format) materials uses the giant_hydro build
+VARIANT_CONFIG = {"giant_aneos": "giant_hydro"}
+GOLDEN_CASES = [f"{c}{s}" for c in tuple(CONFIGS) + tuple(VARIANT_CONFIG) for s in ("", "_stirred")]
 
 # fields compared against the reference's output.  `depth` is excluded: the reference's value
 # depends on the insertion order of its racy tree build (src/tree.cu:259).
@@ -30,7 +33,8 @@ RTOL = 1e-9   # north_star: "within 1e-9 relative in fp64"
 
 
 def config_of(case: str) -> str:
-    return case[:-8] if case.endswith("_stirred") else case
+    base = case[:-8] if case.endswith("_stirred") else case
+    return VARIANT_CONFIG.get(base, base)
 
 
 def load_golden(case: str):

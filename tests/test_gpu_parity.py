@@ -73,12 +73,14 @@ def test_cuda_matches_reference_golden(case):
                 assert np.array_equal(out[name], ref), f"{stage}: {name}"
 
 
-ORACLE_SIZES = {"shocktube": 20000, "sedov": 40000, "rings": 40000, "impact": 30000, "giant_hydro": 30000, "giant_solid": 30000}
+ORACLE_SIZES = {"shocktube": 20000, "sedov": 40000, "rings": 40000, "impact": 30000, "giant_hydro": 30000, "giant_solid": 30000,
+                "giant_aneos": 30000}
 
 
-@pytest.mark.parametrize("config", common.CONFIGS)
-def test_cuda_matches_oracle_larger(config, tmp_path):
-    sc = scenarios.make(config, ORACLE_SIZES[config], stirred=True)
+@pytest.mark.parametrize("scenario", tuple(common.CONFIGS) + tuple(common.VARIANT_CONFIG))
+def test_cuda_matches_oracle_larger(scenario, tmp_path):
+    sc = scenarios.make(scenario, ORACLE_SIZES[scenario], stirred=True)
+    config = sc.config
     cfg = state.write_material_files(sc, str(tmp_path))
     mats = api.MaterialTables(config, cfg)
     arrays, meta = state.scenario_arrays(sc, mats)
