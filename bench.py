@@ -271,6 +271,13 @@ def main() -> None:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     total_ms = float(t.item())
     total_particles = float(cnt.item())
+    # per-rank picture (owned, halo, ms in b200sph_rhs_eval, ms in the exchange incl. waiting for peers): shows imbalance
+    mine = torch.tensor([float(n), float(drhs.n_total - n), stage_ms.get("ms_total", 0.0) / args.steps, exch_ms / args.steps],
+                        dtype=torch.float64, device="cuda")
+    per_rank = [mine.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    per_rank = [[round(float(x), 4) for x in row.tolist()] for row in per_rank]
     value = total_particles * args.steps / (total_ms * 1e-3)
 
     # ---- end to end: host (pinned) buffers, copies inside the timed region.
@@ -370,7 +377,8 @@ def main() -> None:
                                  % (drhs.halo.levels, ", replicated gravity tree (NCCL all_gather of x,y,z,m)" if meta["selfgravity"] else ""))
                    if world > 1 else "single",
                    "rank0": {"owned": n, "halo": drhs.n_total - n, "halo_bytes_sent": drhs.halo.last.get("bytes_sent", 0),
-                             "exchange_ms_per_step": exch_ms / args.steps}},
+                             "exchange_ms_per_step": exch_ms / args.steps},
+                   "ranks": {"columns": ["owned", "halo", "rhs_ms", "exchange_ms"], "rows": per_rank}},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "search_grid": {"cells": stats["n_cells"], "cell_size": stats["cell_size"], "max_interactions": stats["max_noi"]},

@@ -136,15 +136,21 @@ extern "C" int b200sph_halo_box_hmax(b200sph_handle *h, const double *x, const d
     return B200SPH_OK;
 }
 
-/* ------------------------------------------------------------------ who needs which particle */
+/* ------------------------------------------------------------------ who needs which particle
+ * Two-stage test: a rank is looked at only when the particle is within reach of the bounding box of ALL its
+ * boxes (with the largest `extra` among them); then its boxes are tested one by one.  Interior particles --
+ * the vast majority -- cost n_ranks - 1 tests instead of one per box of every rank. */
 __global__ void __launch_bounds__(HALO_THREADS)
 h_mask(const double *x, const double *y, const double *z, const double *sml, int n, const HaloDomains *dom, const double *extra,
        int extra_stride, unsigned long long *mask_out, int *blk_counts, int n_blocks)
 {
-    extern __shared__ double sh_box[];   /* n_boxes x {lo[3], hi[3], extra} and the owner ids behind them */
+    extern __shared__ double sh_box[];   /* n_boxes x {lo[3], hi[3], extra}, n_ranks x {lo[3], hi[3], extra}, then int tables */
     const int n_boxes = dom->n_boxes, n_ranks = dom->n_ranks, my_rank = dom->my_rank;
     double *bx = sh_box;
-    int *br = reinterpret_cast<int *>(sh_box + 7 * n_boxes);
+    double *rb = sh_box + 7 * n_boxes;
+    int *first = reinterpret_cast<int *>(rb + 7 * n_ranks);   /* first box of rank r (n_boxes for a rank without boxes) */
+    for (int r = threadIdx.x; r <= n_ranks; r += blockDim.x) first[r] = n_boxes;
+    __syncthreads();
     for (int b = threadIdx.x; b < n_boxes; b += blockDim.x) {
         const int r = dom->rank[b];
         for (int a = 0; a < 3; a++) {
@@ -152,7 +158,20 @@ h_mask(const double *x, const double *y, const double *z, const double *sml, int
             bx[7 * b + 3 + a] = dom->hi[b][a];
         }
         bx[7 * b + 6] = extra ? extra[r * extra_stride + dom->local[b]] : 0.0;
-        br[b] = r;
+        if (dom->local[b] == 0) first[r] = b;   /* box_rank is non-decreasing: a rank's boxes are contiguous */
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < n_ranks; r += blockDim.x) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, ex = 0.0;
+        for (int b = first[r]; b < n_boxes && dom->rank[b] == r; b++) {
+            for (int a = 0; a < 3; a++) {
+                lo[a] = fmin(lo[a], bx[7 * b + a]);
+                hi[a] = fmax(hi[a], bx[7 * b + 3 + a]);
+            }
+            ex = fmax(ex, bx[7 * b + 6]);
+        }
+        for (int a = 0; a < 3; a++) { rb[7 * r + a] = lo[a]; rb[7 * r + 3 + a] = hi[a]; }
+        rb[7 * r + 6] = ex;
     }
     __syncthreads();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,17 +179,29 @@ h_mask(const double *x, const double *y, const double *z, const double *sml, int
     if (k < n) {
         const double p[3] = {x[k], (DIM > 1 && y) ? y[k] : 0.0, (DIM > 2 && z) ? z[k] : 0.0};
         const double hk = sml[k];
-        for (int b = 0; b < n_boxes; b++) {
-            const int r = br[b];
-            if (r == my_rank || ((mask >> r) & 1ull)) continue;
+        for (int r = 0; r < n_ranks; r++) {
+            if (r == my_rank) continue;
             double d2 = 0.0;
 #pragma unroll
             for (int a = 0; a < DIM; a++) {
-                const double g = fmax(fmax(bx[7 * b + a] - p[a], p[a] - bx[7 * b + 3 + a]), 0.0);
+                const double g = fmax(fmax(rb[7 * r + a] - p[a], p[a] - rb[7 * r + 3 + a]), 0.0);
                 d2 = fma(g, g, d2);
             }
-            const double reach = (hk + bx[7 * b + 6]) * (1.0 + 1e-9);
-            if (d2 < reach * reach) mask |= 1ull << r;
+            const double far = (hk + rb[7 * r + 6]) * (1.0 + 1e-9);
+            if (!(d2 < far * far)) continue;
+            for (int b = first[r]; b < n_boxes && dom->rank[b] == r; b++) {
+                d2 = 0.0;
+#pragma unroll
+                for (int a = 0; a < DIM; a++) {
+                    const double g = fmax(fmax(bx[7 * b + a] - p[a], p[a] - bx[7 * b + 3 + a]), 0.0);
+                    d2 = fma(g, g, d2);
+                }
+                const double reach = (hk + bx[7 * b + 6]) * (1.0 + 1e-9);
+                if (d2 < reach * reach) {
+                    mask |= 1ull << r;
+                    break;
+                }
+            }
         }
         mask_out[k] = mask;
     }
@@ -248,7 +279,7 @@ extern "C" int b200sph_halo_select(b200sph_handle *h, const double *x, const dou
     if (halo_scratch(h, st, n)) return B200SPH_ERR_CUDA;
     const int n_blocks = (n + HALO_THREADS - 1) / HALO_THREADS;
     const HaloDomains &d = st->host;
-    const size_t smem = (size_t)d.n_boxes * (7 * sizeof(double) + sizeof(int));
+    const size_t smem = (size_t)(d.n_boxes + d.n_ranks) * 7 * sizeof(double) + (size_t)(d.n_ranks + 1) * sizeof(int);
     if (smem > 48 * 1024) HCU(cudaFuncSetAttribute(h_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     h_mask<<<n_blocks, HALO_THREADS, smem, h->stream>>>(x, y, z, sml, n, st->dev, extra, extra_stride, st->mask, st->blk_counts, n_blocks);
     h_scan<<<1, 1024, 0, h->stream>>>(st->blk_counts, n_blocks, d.n_ranks, idx_capacity, counts_out);

@@ -1178,10 +1178,19 @@ __device__ __forceinline__ double int_power(double x, int n)
 /* Register budget of the force kernel, measured on a B200 (gpurun_out v4, round 1): the 2-D solid loop gains
  * 11 % from a 128-register cap (4 blocks of 128 threads per SM), the 3-D solid loop loses 50 % to spills. */
 #ifndef B200_FORCES_MIN_BLOCKS
-#define B200_FORCES_MIN_BLOCKS ((SOLID && DIM == 2) ? 4 : 1)
+#if SOLID && DIM == 2
+#define B200_FORCES_MIN_BLOCKS 4
+#else
+#define B200_FORCES_MIN_BLOCKS 1
+#endif
+#endif
+#if B200_FORCES_MIN_BLOCKS > 1
+#define FORCES_BOUNDS __launch_bounds__(128, B200_FORCES_MIN_BLOCKS)
+#else
+#define FORCES_BOUNDS __launch_bounds__(128)   /* not (128, 1): that form makes ptxas take 190 registers for the 3-D solid loop */
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(128, B200_FORCES_MIN_BLOCKS)
+__global__ void FORCES_BOUNDS
 k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -176,7 +176,10 @@ class HaloExchange:
     same test is evaluated with torch ops.
     """
 
-    def __init__(self, fields: dict, capacity: int, dec: MortonDecomposition, levels: int = 2, group=None, engine=None):
+    H_GROWTH = 0.02   # head-room on last evaluation's per-box h_max when h is integrated (VARIABLE_SML / INTEGRATE_SML)
+
+    def __init__(self, fields: dict, capacity: int, dec: MortonDecomposition, levels: int = 2, group=None, engine=None,
+                 h_evolves: bool = True):
         self.fields = fields
         self.capacity = capacity
         self.dec = dec
@@ -197,43 +200,86 @@ class HaloExchange:
         self._send = None
         self._recv = None
         self.last = {}
+        self.last_retry = False
+        self.h_evolves = h_evolves
 
     def _rows(self, name: str) -> torch.Tensor:
         return self.fields[name].view(self.capacity, -1)
 
-    # ------------------------------------------------------------------ GPU path: library kernels, two host reads
+    # ------------------------------------------------------------------ GPU path: library kernels, two collectives, one host wait
+    def _setup_cuda(self, n_owned: int) -> None:
+        f = self.fields
+        dev = f["x"].device
+        eng = self.engine
+        eng.halo_set_domains(self.boxes, self.box_rank, self.world, self.rank)
+        self._desc = eng.halo_fields(f, self.exchange, self.capacity, HALO_ZERO_FIELDS)
+        self.width = eng.halo_row_width(self._desc)
+        nb = self._nb_max = max(self.box_counts)
+        w = self.world
+        self._idx = torch.empty(max(self.capacity, 2 * n_owned), dtype=torch.int32, device=dev)
+        self._counts = torch.zeros(w + 1, dtype=torch.int32, device=dev)
+        # one row per rank: [largest h in each of its boxes (nb), rows it sends to every rank (w), send list overflow (1)]
+        self._meta_mine = torch.zeros(nb + w + 1, dtype=torch.float64, device=dev)
+        self._meta_all = torch.zeros(w * (nb + w + 1), dtype=torch.float64, device=dev)
+        self._meta_host = torch.zeros(w * (nb + w + 1), dtype=torch.float64).pin_memory()
+        self._hmax_used = None        # device [w * nb]: the per-box h_max the selection works with
+        self._hmax_used_host = None   # the same numbers on the host, for the check after the all-gather
+
+    def _select_and_share(self, n_owned: int):
+        """Selection with the current `_hmax_used`, then ONE all-gather of (fresh box h_max, send counts); returns the host table."""
+        f, eng, nb, w = self.fields, self.engine, self._nb_max, self.world
+        mine = self._meta_mine
+        if self.levels == 2:
+            eng.halo_box_hmax(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, mine[:nb])
+        eng.halo_select(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, self._hmax_used if self.levels == 2 else None, nb,
+                        self._idx, self._counts)
+        mine[nb:].copy_(self._counts)
+        dist.all_gather_into_tensor(self._meta_all, mine, group=self.group)
+        self._meta_host.copy_(self._meta_all, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the only host wait: NCCL needs the split sizes
+        return self._meta_host.view(w, nb + w + 1).numpy()
+
     def _run_cuda(self, n_owned: int) -> int:
+        """Stream-ordered exchange.  The second halo level needs every rank's largest h per box, which used to cost
+        its own all-gather before the selection could start.  Now the selection runs with the values of the
+        previous evaluation (inflated by `H_GROWTH` when h evolves), the fresh values travel in the same all-gather
+        as the send counts, and the exchange is repeated with them only if a box outgrew what was assumed --
+        over-selection is always safe, under-selection never happens."""
         f = self.fields
         dev = f["x"].device
         eng = self.engine
         if eng is None:
             raise RuntimeError("halo exchange on GPU buffers needs the b200sph engine (no torch fallback on the product path)")
         if self._desc is None:
-            eng.halo_set_domains(self.boxes, self.box_rank, self.world, self.rank)
-            self._desc = eng.halo_fields(f, self.exchange, self.capacity, HALO_ZERO_FIELDS)
-            self.width = eng.halo_row_width(self._desc)
-            self._nb_max = max(self.box_counts)
-            self._hmax_mine = torch.zeros(self._nb_max, dtype=torch.float64, device=dev)
-            self._hmax_all = torch.zeros(self.world * self._nb_max, dtype=torch.float64, device=dev)
-            self._idx = torch.empty(max(self.capacity, 2 * n_owned), dtype=torch.int32, device=dev)
-            self._counts = torch.zeros(self.world + 1, dtype=torch.int32, device=dev)
-            self._counts_host = torch.zeros(self.world + 1, dtype=torch.int32).pin_memory()
-            self._recv_counts = torch.zeros(self.world, dtype=torch.int32, device=dev)
-            self._recv_host = torch.zeros(self.world, dtype=torch.int32).pin_memory()
-        extra = None
+            self._setup_cuda(n_owned)
+        nb, w = self._nb_max, self.world
+        if self.levels == 2 and self._hmax_used is None:
+            # first evaluation: fetch the table once, the old way
+            eng.halo_box_hmax(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, self._meta_mine[:nb])
+            first = torch.zeros(w * nb, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(first, self._meta_mine[:nb].contiguous(), group=self.group)
+            self._hmax_used = first
+            self._hmax_used_host = first.cpu().numpy().reshape(w, nb).copy()
+        table = self._select_and_share(n_owned)
+        self.last_retry = False
         if self.levels == 2:
-            eng.halo_box_hmax(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, self._hmax_mine)
-            dist.all_gather_into_tensor(self._hmax_all, self._hmax_mine, group=self.group)
-            extra = self._hmax_all
-        eng.halo_select(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, extra, self._nb_max, self._idx, self._counts)
-        dist.all_to_all_single(self._recv_counts, self._counts[: self.world], group=self.group)
-        self._counts_host.copy_(self._counts, non_blocking=True)
-        self._recv_host.copy_(self._recv_counts, non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the only host wait: NCCL needs the split sizes
-        send_counts = [int(c) for c in self._counts_host[: self.world]]
-        recv_counts = [int(c) for c in self._recv_host]
-        if int(self._counts_host[self.world]) != 0:
-            raise RuntimeError(f"halo send list of {sum(send_counts)} entries does not fit {self._idx.numel()}")
+            fresh = table[:, :nb]
+            if (fresh > self._hmax_used_host).any():
+                # a box holds a larger h than the selection assumed: redo it with the fresh table (exact this time)
+                self._hmax_used = self._meta_all.view(w, -1)[:, :nb].contiguous().view(-1)
+                self._hmax_used_host = fresh.copy()
+                table = self._select_and_share(n_owned)
+                fresh = table[:, :nb]
+                self.last_retry = True
+            # assumption for the next evaluation
+            growth = 1.0 + self.H_GROWTH if self.h_evolves else 1.0
+            self._hmax_used = (self._meta_all.view(w, -1)[:, :nb] * growth).contiguous().view(-1)
+            self._hmax_used_host = fresh * growth
+        counts = table[:, nb: nb + w]
+        if table[:, nb + w].any():
+            raise RuntimeError(f"halo send list of a rank does not fit its index buffer ({self._idx.numel()} entries here)")
+        send_counts = [int(c) for c in counts[self.rank]]
+        recv_counts = [int(c) for c in counts[:, self.rank]]
         n_send, n_recv = sum(send_counts), sum(recv_counts)
         if n_owned + n_recv > self.capacity:
             raise RuntimeError(f"halo of {n_recv} particles does not fit: capacity {self.capacity}, owned {n_owned}")
@@ -381,7 +427,9 @@ class DistributedRhs:
         self.capacity = capacity
         self.n_owned = n_owned
         self.meta = meta
-        self.halo = HaloExchange(fields, capacity, dec, levels=halo_levels(switches), group=group, engine=engine)
+        h_evolves = bool(switches.get("VARIABLE_SML", 0) or switches.get("INTEGRATE_SML", 0))
+        self.halo = HaloExchange(fields, capacity, dec, levels=halo_levels(switches), group=group, engine=engine,
+                                 h_evolves=h_evolves)
         self.gravity = GravitySources(dec.dim, group) if meta.get("selfgravity") else None
         self.n_total = n_owned
 

@@ -33,23 +33,29 @@ def timed(label, fn, acc):
 acc = {}
 reps = 20
 f = dev
+nb, w = hx._nb_max, world
 for _ in range(reps):
     dist.barrier()
-    timed("box_hmax", lambda: eng.halo_box_hmax(f["x"], f.get("y"), f.get("z"), f["h"], n, hx._hmax_mine), acc)
-    timed("all_gather", lambda: dist.all_gather_into_tensor(hx._hmax_all, hx._hmax_mine), acc)
-    timed("select", lambda: eng.halo_select(f["x"], f.get("y"), f.get("z"), f["h"], n, hx._hmax_all, hx._nb_max, hx._idx, hx._counts), acc)
-    timed("a2a_counts", lambda: dist.all_to_all_single(hx._recv_counts, hx._counts[:world]), acc)
-    def rd():
-        hx._counts_host.copy_(hx._counts, non_blocking=True); hx._recv_host.copy_(hx._recv_counts, non_blocking=True)
+    mine = hx._meta_mine
+    timed("box_hmax", lambda: eng.halo_box_hmax(f["x"], f.get("y"), f.get("z"), f["h"], n, mine[:nb]), acc)
+    timed("select", lambda: eng.halo_select(f["x"], f.get("y"), f.get("z"), f["h"], n, hx._hmax_used if hx.levels == 2 else None, nb,
+                                            hx._idx, hx._counts), acc)
+    def share():
+        mine[nb:].copy_(hx._counts)
+        dist.all_gather_into_tensor(hx._meta_all, mine)
+        hx._meta_host.copy_(hx._meta_all, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return [int(c) for c in hx._counts_host[:world]], [int(c) for c in hx._recv_host]
-    sc_, rc_ = timed("read_counts", rd, acc)
+        return hx._meta_host.view(w, nb + w + 1).numpy()
+    table = timed("all_gather_meta+read", share, acc)
+    counts = table[:, nb: nb + w]
+    sc_, rc_ = [int(c) for c in counts[rank]], [int(c) for c in counts[:, rank]]
     ns, nr = sum(sc_), sum(rc_)
     send = hx._send[: ns * hx.width].view(ns, hx.width); recv = hx._recv[: nr * hx.width].view(nr, hx.width)
     timed("pack", lambda: eng.halo_pack(hx._desc, hx._idx, ns, send), acc)
     timed("a2a_data", lambda: dist.all_to_all_single(recv, send, output_split_sizes=rc_, input_split_sizes=sc_), acc)
     timed("unpack", lambda: eng.halo_unpack(hx._desc, recv, nr, n), acc)
+    dist.barrier()
     t0 = time.perf_counter(); hx.run(n); torch.cuda.synchronize(); acc["whole_run"] = acc.get("whole_run", 0.0) + (time.perf_counter() - t0) * 1e3
 if rank == 0:
-    print({k: round(v / reps, 4) for k, v in acc.items()}, "n_send", ns, "width", hx.width, flush=True)
+    print({k: round(v / reps, 4) for k, v in acc.items()}, "n_send", ns, "width", hx.width, "boxes", len(hx.box_rank), "retry", hx.last_retry, flush=True)
 dist.destroy_process_group()
