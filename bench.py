@@ -373,8 +373,11 @@ def main() -> None:
         "config": {"workload": f"{workload} (synthetic, {n_global} particles = {n_global // world} per GPU)", "particles": int(total_particles),
                    "mean_interactions": total_noi / n, "l2": "512 MiB buffer written between timed steps (untimed)",
                    "timing": "per-step CUDA events on the launching stream, summed over K steps, max over ranks",
-                   "multi_gpu": ("Morton-curve domain decomposition, %d-level halo exchange per evaluation (NCCL all_to_all)%s"
-                                 % (drhs.halo.levels, ", replicated gravity tree (NCCL all_gather of x,y,z,m)" if meta["selfgravity"] else ""))
+                   "multi_gpu": ("Morton-curve domain decomposition, %d-level halo exchange per evaluation (NCCL all_to_all of the "
+                                 "packed state; the send plan is reused while no particle moved > %.2f h_min and re-decided otherwise: "
+                                 "%d plan builds, %d stale plans in this run)%s"
+                                 % (drhs.halo.levels, drhs.halo.SKIN, drhs.halo.plan_builds, drhs.halo.stale_plans,
+                                    ", replicated gravity tree (NCCL all_gather of x,y,z,m)" if meta["selfgravity"] else ""))
                    if world > 1 else "single",
                    "rank0": {"owned": n, "halo": drhs.n_total - n, "halo_bytes_sent": drhs.halo.last.get("bytes_sent", 0),
                              "exchange_ms_per_step": exch_ms / args.steps},

@@ -233,6 +233,16 @@ int b200sph_halo_box_hmax(b200sph_handle *h, const double *x, const double *y, c
  * group sizes, counts_out[n_ranks] != 0 if idx_capacity was too small. */
 int b200sph_halo_select(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
                         const double *extra, int extra_stride, int *idx_out, int idx_capacity, int *counts_out);
+/* Selection for a REUSABLE plan: reach = (h_k + extra) * reach_scale + skin.  A list built with
+ * reach_scale = 1 + growth and skin = 2 * max_move stays complete while b200sph_halo_plan_check() reports no violation. */
+int b200sph_halo_select_plan(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
+                             const double *extra, int extra_stride, double reach_scale, double skin, int *idx_out,
+                             int idx_capacity, int *counts_out);
+/* *flag_out (device int) = 1 if a particle is further than max_move from its position (x0, y0, z0) at plan time or
+ * its smoothing length exceeds sml0 * (1 + growth), else 0.  Stream-ordered, no host synchronisation. */
+int b200sph_halo_plan_check(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml,
+                            const double *x0, const double *y0, const double *z0, const double *sml0, int n,
+                            double max_move, double growth, int *flag_out);
 /* One member of the reference's struct Particle taking part in the exchange: `per` values per particle;
  * kind 0 = double, 1 = int32 (transported as double), 2 = int32 that is not transported but zeroed on the
  * received rows (numFlaws, numActiveFlaws: the flaw lists of halo copies are never read). */
@@ -247,6 +257,13 @@ int b200sph_halo_row_width(const b200sph_halo_field *fields, int n_fields);
 int b200sph_halo_pack(b200sph_handle *h, const b200sph_halo_field *fields, int n_fields, const int *idx, int n_rows, double *out);
 /* particle rows [first_row, first_row + n_rows) <- in[row * width + col] */
 int b200sph_halo_unpack(b200sph_handle *h, const b200sph_halo_field *fields, int n_fields, const double *in, int n_rows, int first_row);
+/* The same with the block of every rank stored column by column (a warp then walks one member array):
+ * counts[r] (device, n_ranks ints) = rows going to / coming from rank r, in rank order; a rank's block starts at
+ * (rows of lower ranks) * width and holds its columns one after the other. */
+int b200sph_halo_pack_by_rank(b200sph_handle *h, const b200sph_halo_field *fields, int n_fields, const int *idx,
+                              const int *counts, int n_ranks, int n_rows, double *out);
+int b200sph_halo_unpack_by_rank(b200sph_handle *h, const b200sph_halo_field *fields, int n_fields, const double *in,
+                                const int *counts, int n_ranks, int n_rows, int first_row);
 /* Multi-GPU self-gravity with a replicated tree.  x,y,z,m (device pointers, n_sources doubles each; y/z may
  * be NULL below DIM 2/3) describe the WHOLE particle set in a rank-independent order, normally the
  * all-gather of every rank's owned particles; the caller's owned particles are the block

@@ -130,9 +130,15 @@ _EXPORTS = {
     "b200sph_halo_box_hmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "b200sph_halo_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                       C.c_void_p, C.c_int, C.c_void_p]),
+    "b200sph_halo_select_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                           C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200sph_halo_plan_check": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]),
     "b200sph_halo_row_width": (C.c_int, [C.c_void_p, C.c_int]),
     "b200sph_halo_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "b200sph_halo_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "b200sph_halo_pack_by_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "b200sph_halo_unpack_by_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "b200sph_set_gravity_sources": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
 }
 _LIBS: dict = {}
@@ -356,6 +362,16 @@ class RhsEngine:
                                                  _ptr_of(extra) or None, extra_stride, _ptr_of(idx_out), int(idx_out.numel()),
                                                  _ptr_of(counts_out)))
 
+    def halo_select_plan(self, x, y, z, h, n: int, extra, extra_stride: int, reach_scale: float, skin: float, idx_out, counts_out) -> None:
+        self._check(self.lib.b200sph_halo_select_plan(self.handle, _ptr_of(x), _ptr_of(y) or None, _ptr_of(z) or None, _ptr_of(h), n,
+                                                      _ptr_of(extra) or None, extra_stride, float(reach_scale), float(skin),
+                                                      _ptr_of(idx_out), int(idx_out.numel()), _ptr_of(counts_out)))
+
+    def halo_plan_check(self, x, y, z, h, x0, y0, z0, h0, n: int, max_move: float, growth: float, flag_out) -> None:
+        self._check(self.lib.b200sph_halo_plan_check(self.handle, _ptr_of(x), _ptr_of(y) or None, _ptr_of(z) or None, _ptr_of(h),
+                                                     _ptr_of(x0), _ptr_of(y0) or None, _ptr_of(z0) or None, _ptr_of(h0), n,
+                                                     float(max_move), float(growth), _ptr_of(flag_out)))
+
     @staticmethod
     def halo_fields(fields: dict, names, capacity: int, zero_names=()):
         """ctypes array of b200sph_halo_field for the named members of `fields` (flat tensors sized for `capacity`)."""
@@ -376,6 +392,14 @@ class RhsEngine:
 
     def halo_unpack(self, desc, buf, n_rows: int, first_row: int) -> None:
         self._check(self.lib.b200sph_halo_unpack(self.handle, desc, len(desc), _ptr_of(buf), n_rows, first_row))
+
+    def halo_pack_by_rank(self, desc, idx, counts, n_ranks: int, n_rows: int, out) -> None:
+        self._check(self.lib.b200sph_halo_pack_by_rank(self.handle, desc, len(desc), _ptr_of(idx), _ptr_of(counts), n_ranks, n_rows,
+                                                       _ptr_of(out)))
+
+    def halo_unpack_by_rank(self, desc, buf, counts, n_ranks: int, n_rows: int, first_row: int) -> None:
+        self._check(self.lib.b200sph_halo_unpack_by_rank(self.handle, desc, len(desc), _ptr_of(buf), _ptr_of(counts), n_ranks, n_rows,
+                                                         first_row))
 
     def set_gravity_sources(self, x, y, z, m, n_sources: int, own_begin: int) -> None:
         """Multi-GPU gravity: device arrays of the global particle set (see include/b200sph.h)."""

@@ -142,7 +142,7 @@ extern "C" int b200sph_halo_box_hmax(b200sph_handle *h, const double *x, const d
  * the vast majority -- cost n_ranks - 1 tests instead of one per box of every rank. */
 __global__ void __launch_bounds__(HALO_THREADS)
 h_mask(const double *x, const double *y, const double *z, const double *sml, int n, const HaloDomains *dom, const double *extra,
-       int extra_stride, unsigned long long *mask_out, int *blk_counts, int n_blocks)
+       int extra_stride, double reach_scale, double skin, unsigned long long *mask_out, int *blk_counts, int n_blocks)
 {
     extern __shared__ double sh_box[];   /* n_boxes x {lo[3], hi[3], extra}, n_ranks x {lo[3], hi[3], extra}, then int tables */
     const int n_boxes = dom->n_boxes, n_ranks = dom->n_ranks, my_rank = dom->my_rank;
@@ -187,7 +187,7 @@ h_mask(const double *x, const double *y, const double *z, const double *sml, int
                 const double g = fmax(fmax(rb[7 * r + a] - p[a], p[a] - rb[7 * r + 3 + a]), 0.0);
                 d2 = fma(g, g, d2);
             }
-            const double far = (hk + rb[7 * r + 6]) * (1.0 + 1e-9);
+            const double far = (hk + rb[7 * r + 6]) * reach_scale * (1.0 + 1e-9) + skin;
             if (!(d2 < far * far)) continue;
             for (int b = first[r]; b < n_boxes && dom->rank[b] == r; b++) {
                 d2 = 0.0;
@@ -196,7 +196,7 @@ h_mask(const double *x, const double *y, const double *z, const double *sml, int
                     const double g = fmax(fmax(bx[7 * b + a] - p[a], p[a] - bx[7 * b + 3 + a]), 0.0);
                     d2 = fma(g, g, d2);
                 }
-                const double reach = (hk + bx[7 * b + 6]) * (1.0 + 1e-9);
+                const double reach = (hk + bx[7 * b + 6]) * reach_scale * (1.0 + 1e-9) + skin;
                 if (d2 < reach * reach) {
                     mask |= 1ull << r;
                     break;
@@ -270,9 +270,21 @@ h_write(const unsigned long long *mask, int n, int n_ranks, const int *blk_offse
     }
 }
 
+extern "C" int b200sph_halo_select_plan(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
+                                        const double *extra, int extra_stride, double reach_scale, double skin, int *idx_out,
+                                        int idx_capacity, int *counts_out);
+
 extern "C" int b200sph_halo_select(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
                                    const double *extra, int extra_stride, int *idx_out, int idx_capacity, int *counts_out)
 {
+    return b200sph_halo_select_plan(h, x, y, z, sml, n, extra, extra_stride, 1.0, 0.0, idx_out, idx_capacity, counts_out);
+}
+
+extern "C" int b200sph_halo_select_plan(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml, int n,
+                                        const double *extra, int extra_stride, double reach_scale, double skin, int *idx_out,
+                                        int idx_capacity, int *counts_out)
+{
+    if (!(reach_scale >= 1.0) || !(skin >= 0.0)) return B200SPH_ERR_BAD_ARGUMENT;
     HaloState *st = h ? (HaloState *)h->halo : nullptr;
     if (!st || !x || !sml || !idx_out || !counts_out || n <= 0) return B200SPH_ERR_BAD_ARGUMENT;
     HCU(cudaSetDevice(h->device));
@@ -281,9 +293,43 @@ extern "C" int b200sph_halo_select(b200sph_handle *h, const double *x, const dou
     const HaloDomains &d = st->host;
     const size_t smem = (size_t)(d.n_boxes + d.n_ranks) * 7 * sizeof(double) + (size_t)(d.n_ranks + 1) * sizeof(int);
     if (smem > 48 * 1024) HCU(cudaFuncSetAttribute(h_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    h_mask<<<n_blocks, HALO_THREADS, smem, h->stream>>>(x, y, z, sml, n, st->dev, extra, extra_stride, st->mask, st->blk_counts, n_blocks);
+    h_mask<<<n_blocks, HALO_THREADS, smem, h->stream>>>(x, y, z, sml, n, st->dev, extra, extra_stride, reach_scale, skin, st->mask,
+                                                        st->blk_counts, n_blocks);
     h_scan<<<1, 1024, 0, h->stream>>>(st->blk_counts, n_blocks, d.n_ranks, idx_capacity, counts_out);
     h_write<<<n_blocks, HALO_THREADS, 0, h->stream>>>(st->mask, n, d.n_ranks, st->blk_counts, n_blocks, idx_capacity, idx_out);
+    HCU(cudaGetLastError());
+    return B200SPH_OK;
+}
+
+/* ------------------------------------------------------------------ is a send plan still valid?
+ * A plan (send list + counts) built with reach (h_k + extra) * (1 + growth) + 2 * max_move stays complete while no
+ * particle has moved further than max_move from where it was when the plan was built and no smoothing length
+ * has grown by more than `growth`.  One flag for all particles; the host all-reduces it over the ranks. */
+__global__ void __launch_bounds__(HALO_THREADS)
+h_plan_check(const double *x, const double *y, const double *z, const double *sml, const double *x0, const double *y0, const double *z0,
+             const double *sml0, int n, double max_move2, double growth, int *flag)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (k < n) {
+        double d2 = (x[k] - x0[k]) * (x[k] - x0[k]);
+        if (DIM > 1 && y) d2 += (y[k] - y0[k]) * (y[k] - y0[k]);
+        if (DIM > 2 && z) d2 += (z[k] - z0[k]) * (z[k] - z0[k]);
+        bad = !(d2 <= max_move2) || !(sml[k] <= sml0[k] * (1.0 + growth));   /* NaNs count as a violation */
+    }
+    if (__syncthreads_or((int)bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+extern "C" int b200sph_halo_plan_check(b200sph_handle *h, const double *x, const double *y, const double *z, const double *sml,
+                                       const double *x0, const double *y0, const double *z0, const double *sml0, int n,
+                                       double max_move, double growth, int *flag_out)
+{
+    if (!h || !x || !sml || !x0 || !sml0 || !flag_out || n < 0 || !(max_move >= 0.0) || !(growth >= 0.0)) return B200SPH_ERR_BAD_ARGUMENT;
+    HCU(cudaSetDevice(h->device));
+    HCU(cudaMemsetAsync(flag_out, 0, sizeof(int), h->stream));
+    if (n > 0)
+        h_plan_check<<<(n + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, 0, h->stream>>>(x, y, z, sml, x0, y0, z0, sml0, n,
+                                                                                             max_move * max_move, growth, flag_out);
     HCU(cudaGetLastError());
     return B200SPH_OK;
 }
@@ -357,6 +403,99 @@ extern "C" int b200sph_halo_row_width(const b200sph_halo_field *fields, int n_fi
     for (int q = 0; fields && q < n_fields; q++)
         if (fields[q].data && fields[q].per > 0 && fields[q].kind != 2) w += fields[q].per;
     return w;
+}
+
+/* ------------------------------------------------------------------ pack / unpack, column-major per rank
+ * Row-major rows make every warp touch `width` different arrays at once (153 us for 48 MB on the impact case,
+ * a tenth of the HBM rate).  Here the block of rows going to (coming from) one rank is stored column by column:
+ *     buffer = [rank 0: col 0 rows.. | col 1 rows.. | ...][rank 1: ...]
+ * so a warp walks ONE member array along ascending particle indices and writes one contiguous run.  The blocks
+ * of different ranks stay contiguous, which is all all_to_all needs (split sizes = rows * width). */
+__device__ __forceinline__ int rank_of_row(const int *prefix, int n_ranks, int g)
+{
+    int r = 0;
+    while (r + 1 < n_ranks && g >= prefix[r + 1]) r++;
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+h_pack_cols(HaloFields f, const int *idx, const int *counts, int n_ranks, int n_rows, double *out)
+{
+    __shared__ int prefix[HALO_MAX_RANKS + 1];
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int r = 0; r < n_ranks; r++) { prefix[r] = run; run += counts[r]; }
+        prefix[n_ranks] = run;
+    }
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_rows * f.width) return;
+    const int c = (int)(t / n_rows), g = (int)(t % n_rows);
+    int q = 0;
+    while (c >= f.col[q + 1]) q++;
+    const int comp = c - f.col[q];
+    const int r = rank_of_row(prefix, n_ranks, g);
+    const int cnt = prefix[r + 1] - prefix[r];
+    const size_t src = (size_t)idx[g] * f.per[q] + comp;
+    const double v = (f.kind[q] == 0) ? reinterpret_cast<const double *>(f.data[q])[src] : (double)reinterpret_cast<const int *>(f.data[q])[src];
+    out[(size_t)prefix[r] * f.width + (size_t)c * cnt + (g - prefix[r])] = v;
+}
+
+__global__ void __launch_bounds__(256)
+h_unpack_cols(HaloFields f, const double *in, const int *counts, int n_ranks, int n_rows, int first_row)
+{
+    __shared__ int prefix[HALO_MAX_RANKS + 1];
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int r = 0; r < n_ranks; r++) { prefix[r] = run; run += counts[r]; }
+        prefix[n_ranks] = run;
+    }
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_rows * f.width) return;
+    const int c = (int)(t / n_rows), g = (int)(t % n_rows);
+    int q = 0;
+    while (c >= f.col[q + 1]) q++;
+    const int comp = c - f.col[q];
+    const int r = rank_of_row(prefix, n_ranks, g);
+    const int cnt = prefix[r + 1] - prefix[r];
+    const double v = in[(size_t)prefix[r] * f.width + (size_t)c * cnt + (g - prefix[r])];
+    const size_t dst = (size_t)(first_row + g) * f.per[q] + comp;
+    if (f.kind[q] == 0) reinterpret_cast<double *>(f.data[q])[dst] = v;
+    else reinterpret_cast<int *>(f.data[q])[dst] = (int)v;
+}
+
+extern "C" int b200sph_halo_pack_by_rank(b200sph_handle *h, const b200sph_halo_field *fields, int n_fields, const int *idx,
+                                         const int *counts, int n_ranks, int n_rows, double *out)
+{
+    if (!h || !idx || !out || !counts || n_rows < 0 || n_ranks <= 0 || n_ranks > HALO_MAX_RANKS) return B200SPH_ERR_BAD_ARGUMENT;
+    HaloFields f;
+    if (int rc = halo_fields(h, fields, n_fields, f)) return rc;
+    if (n_rows == 0 || f.width == 0) return B200SPH_OK;
+    HCU(cudaSetDevice(h->device));
+    const long long total = (long long)n_rows * f.width;
+    h_pack_cols<<<(unsigned int)((total + 255) / 256), 256, 0, h->stream>>>(f, idx, counts, n_ranks, n_rows, out);
+    HCU(cudaGetLastError());
+    return B200SPH_OK;
+}
+
+extern "C" int b200sph_halo_unpack_by_rank(b200sph_handle *h, const b200sph_halo_field *fields, int n_fields, const double *in,
+                                           const int *counts, int n_ranks, int n_rows, int first_row)
+{
+    if (!h || !in || !counts || n_rows < 0 || first_row < 0 || n_ranks <= 0 || n_ranks > HALO_MAX_RANKS) return B200SPH_ERR_BAD_ARGUMENT;
+    HaloFields f;
+    if (int rc = halo_fields(h, fields, n_fields, f)) return rc;
+    if (n_rows == 0) return B200SPH_OK;
+    HCU(cudaSetDevice(h->device));
+    if (f.width > 0) {
+        const long long total = (long long)n_rows * f.width;
+        h_unpack_cols<<<(unsigned int)((total + 255) / 256), 256, 0, h->stream>>>(f, in, counts, n_ranks, n_rows, first_row);
+    }
+    for (int q = 0; q < n_fields; q++)
+        if (fields[q].data && fields[q].kind == 2 && fields[q].per > 0)
+            h_zero_rows<<<(n_rows * fields[q].per + 255) / 256, 256, 0, h->stream>>>((int *)fields[q].data, fields[q].per, n_rows, first_row);
+    HCU(cudaGetLastError());
+    return B200SPH_OK;
 }
 
 extern "C" int b200sph_halo_pack(b200sph_handle *h, const b200sph_halo_field *fields, int n_fields, const int *idx, int n_rows, double *out)

@@ -176,10 +176,11 @@ class HaloExchange:
     same test is evaluated with torch ops.
     """
 
-    H_GROWTH = 0.02   # head-room on last evaluation's per-box h_max when h is integrated (VARIABLE_SML / INTEGRATE_SML)
+    H_GROWTH = 0.02   # growth of a smoothing length a plan tolerates (only when h is integrated: VARIABLE_SML / INTEGRATE_SML)
+    SKIN = 0.15       # a plan tolerates every particle moving this fraction of the smallest smoothing length
 
     def __init__(self, fields: dict, capacity: int, dec: MortonDecomposition, levels: int = 2, group=None, engine=None,
-                 h_evolves: bool = True):
+                 h_evolves: bool = True, reuse_plan: bool = True):
         self.fields = fields
         self.capacity = capacity
         self.dec = dec
@@ -200,13 +201,30 @@ class HaloExchange:
         self._send = None
         self._recv = None
         self.last = {}
-        self.last_retry = False
         self.h_evolves = h_evolves
+        self.reuse_plan = reuse_plan
+        self._plan = None
+        self.plan_builds = 0
+        self.stale_plans = 0          # evaluations whose plan had gone stale (re-decided before the evaluation ran)
+        self._flag_host = None
 
     def _rows(self, name: str) -> torch.Tensor:
         return self.fields[name].view(self.capacity, -1)
 
-    # ------------------------------------------------------------------ GPU path: library kernels, two collectives, one host wait
+    # ------------------------------------------------------------------ GPU path: reusable send plan, library kernels
+    #
+    # Deciding WHO needs WHICH particle costs three collectives and a host wait (per-box h_max, send counts, and the
+    # split sizes NCCL wants on the host) -- 0.3 ms at 2 ranks, 1.3 ms at 8 for 10^6 particles per rank
+    # (profiles/r01_bench_sedov_{2,8}gpu.json), as much as the evaluation itself.  But the answer changes slowly:
+    # between the three evaluations of an RK step, and between consecutive steps, particles move a small fraction
+    # of h.  So the decision is made once with head-room and REUSED:
+    #
+    #   build  reach = (h_k + h_max(box)) * (1 + growth) + 2 D,  D = SKIN * (smallest h anywhere); snapshot x, h
+    #   reuse  valid while no particle on any rank has moved further than D from its snapshot and no h has grown by
+    #          more than `growth` -- one kernel and one 4-byte all-reduce; the host waits for that verdict only
+    #          (the rows already move behind it, speculatively) and re-decides when it is negative.
+    #
+    # A reused exchange is check -> pack -> all_to_all -> unpack with host-known sizes.
     def _setup_cuda(self, n_owned: int) -> None:
         f = self.fields
         dev = f["x"].device
@@ -214,72 +232,36 @@ class HaloExchange:
         eng.halo_set_domains(self.boxes, self.box_rank, self.world, self.rank)
         self._desc = eng.halo_fields(f, self.exchange, self.capacity, HALO_ZERO_FIELDS)
         self.width = eng.halo_row_width(self._desc)
-        nb = self._nb_max = max(self.box_counts)
-        w = self.world
+        self._nb_max = max(self.box_counts)
         self._idx = torch.empty(max(self.capacity, 2 * n_owned), dtype=torch.int32, device=dev)
-        self._counts = torch.zeros(w + 1, dtype=torch.int32, device=dev)
-        # one row per rank: [largest h in each of its boxes (nb), rows it sends to every rank (w), send list overflow (1)]
-        self._meta_mine = torch.zeros(nb + w + 1, dtype=torch.float64, device=dev)
-        self._meta_all = torch.zeros(w * (nb + w + 1), dtype=torch.float64, device=dev)
-        self._meta_host = torch.zeros(w * (nb + w + 1), dtype=torch.float64).pin_memory()
-        self._hmax_used = None        # device [w * nb]: the per-box h_max the selection works with
-        self._hmax_used_host = None   # the same numbers on the host, for the check after the all-gather
+        self._counts = torch.zeros(self.world + 1, dtype=torch.int32, device=dev)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._flag_event = torch.cuda.Event()
 
-    def _select_and_share(self, n_owned: int):
-        """Selection with the current `_hmax_used`, then ONE all-gather of (fresh box h_max, send counts); returns the host table."""
+    def _build_plan(self, n_owned: int) -> None:
         f, eng, nb, w = self.fields, self.engine, self._nb_max, self.world
-        mine = self._meta_mine
-        if self.levels == 2:
-            eng.halo_box_hmax(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, mine[:nb])
-        eng.halo_select(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, self._hmax_used if self.levels == 2 else None, nb,
-                        self._idx, self._counts)
-        mine[nb:].copy_(self._counts)
-        dist.all_gather_into_tensor(self._meta_all, mine, group=self.group)
-        self._meta_host.copy_(self._meta_all, non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the only host wait: NCCL needs the split sizes
-        return self._meta_host.view(w, nb + w + 1).numpy()
-
-    def _run_cuda(self, n_owned: int) -> int:
-        """Stream-ordered exchange.  The second halo level needs every rank's largest h per box, which used to cost
-        its own all-gather before the selection could start.  Now the selection runs with the values of the
-        previous evaluation (inflated by `H_GROWTH` when h evolves), the fresh values travel in the same all-gather
-        as the send counts, and the exchange is repeated with them only if a box outgrew what was assumed --
-        over-selection is always safe, under-selection never happens."""
-        f = self.fields
         dev = f["x"].device
-        eng = self.engine
-        if eng is None:
-            raise RuntimeError("halo exchange on GPU buffers needs the b200sph engine (no torch fallback on the product path)")
-        if self._desc is None:
-            self._setup_cuda(n_owned)
-        nb, w = self._nb_max, self.world
-        if self.levels == 2 and self._hmax_used is None:
-            # first evaluation: fetch the table once, the old way
-            eng.halo_box_hmax(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, self._meta_mine[:nb])
-            first = torch.zeros(w * nb, dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(first, self._meta_mine[:nb].contiguous(), group=self.group)
-            self._hmax_used = first
-            self._hmax_used_host = first.cpu().numpy().reshape(w, nb).copy()
-        table = self._select_and_share(n_owned)
-        self.last_retry = False
+        growth = self.H_GROWTH if self.h_evolves else 0.0
+        # D: the same number on every rank
+        hmin = f["h"][:n_owned].min().reshape(1).clone() if n_owned > 0 else torch.full((1,), float("inf"), dtype=torch.float64, device=dev)
+        dist.all_reduce(hmin, op=dist.ReduceOp.MIN, group=self.group)
+        extra = None
         if self.levels == 2:
-            fresh = table[:, :nb]
-            if (fresh > self._hmax_used_host).any():
-                # a box holds a larger h than the selection assumed: redo it with the fresh table (exact this time)
-                self._hmax_used = self._meta_all.view(w, -1)[:, :nb].contiguous().view(-1)
-                self._hmax_used_host = fresh.copy()
-                table = self._select_and_share(n_owned)
-                fresh = table[:, :nb]
-                self.last_retry = True
-            # assumption for the next evaluation
-            growth = 1.0 + self.H_GROWTH if self.h_evolves else 1.0
-            self._hmax_used = (self._meta_all.view(w, -1)[:, :nb] * growth).contiguous().view(-1)
-            self._hmax_used_host = fresh * growth
-        counts = table[:, nb: nb + w]
-        if table[:, nb + w].any():
+            mine = torch.zeros(nb, dtype=torch.float64, device=dev)
+            eng.halo_box_hmax(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, mine)
+            extra = torch.zeros(w * nb, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(extra, mine, group=self.group)
+        max_move = self.SKIN * float(hmin.item())
+        eng.halo_select_plan(f["x"], f.get("y"), f.get("z"), f["h"], n_owned, extra, nb, 1.0 + growth, 2.0 * max_move,
+                             self._idx, self._counts)
+        all_counts = torch.zeros(w * (w + 1), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_counts, self._counts, group=self.group)
+        table = all_counts.cpu().numpy().reshape(w, w + 1)
+        if table[:, w].any():
             raise RuntimeError(f"halo send list of a rank does not fit its index buffer ({self._idx.numel()} entries here)")
-        send_counts = [int(c) for c in counts[self.rank]]
-        recv_counts = [int(c) for c in counts[:, self.rank]]
+        send_counts = [int(c) for c in table[self.rank, :w]]
+        recv_counts = [int(c) for c in table[:w, self.rank]]
         n_send, n_recv = sum(send_counts), sum(recv_counts)
         if n_owned + n_recv > self.capacity:
             raise RuntimeError(f"halo of {n_recv} particles does not fit: capacity {self.capacity}, owned {n_owned}")
@@ -287,13 +269,63 @@ class HaloExchange:
             self._send = torch.empty(int(n_send * self.width * 1.2) + 64, dtype=torch.float64, device=dev)
         if self._recv is None or self._recv.numel() < n_recv * self.width:
             self._recv = torch.empty(int(n_recv * self.width * 1.2) + 64, dtype=torch.float64, device=dev)
-        send = self._send[: n_send * self.width].view(n_send, self.width)
-        recv = self._recv[: n_recv * self.width].view(n_recv, self.width)
-        eng.halo_pack(self._desc, self._idx, n_send, send)
-        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=self.group)
-        eng.halo_unpack(self._desc, recv, n_recv, n_owned)
-        self.last = dict(n_halo=n_recv, sent=n_send, bytes_sent=n_send * self.width * 8)
-        return n_owned + n_recv
+        snap = {a: f[a][:n_owned].clone() for a in self.axes + ["h"]}
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+        self._plan = dict(n_owned=n_owned, send_counts=send_counts, recv_counts=recv_counts, n_send=n_send, n_recv=n_recv,
+                          send_counts_dev=i32(send_counts), recv_counts_dev=i32(recv_counts),
+                          max_move=max_move, growth=growth, snap=snap)
+        self._flag_host.zero_()
+        self.plan_builds += 1
+
+    def _check_plan(self, n_owned: int) -> None:
+        """Queue the validity check of the current plan (kernel + 4-byte all-reduce + async read-back); no host wait."""
+        f, pl = self.fields, self._plan
+        sn = pl["snap"]
+        self.engine.halo_plan_check(f["x"], f.get("y"), f.get("z"), f["h"], sn["x"], sn.get("y"), sn.get("z"), sn["h"], n_owned,
+                                    pl["max_move"], pl["growth"], self._flag)
+        dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.group)
+        self._flag_host.copy_(self._flag, non_blocking=True)
+
+    def invalidate(self) -> None:
+        """Drop the plan (the owned set changed, or a check failed): the next run() decides again."""
+        self._plan = None
+
+    def _move_rows(self, n_owned: int) -> None:
+        """pack -> all_to_all -> unpack with the plan's (host-known) sizes; nothing here waits for the device."""
+        pl, eng = self._plan, self.engine
+        n_send, n_recv = pl["n_send"], pl["n_recv"]
+        w, width = self.world, self.width
+        send = self._send[: n_send * width]
+        recv = self._recv[: n_recv * width]
+        # every rank's block is stored column by column (b200sph_halo_pack_by_rank); split sizes are in elements
+        eng.halo_pack_by_rank(self._desc, self._idx, pl["send_counts_dev"], w, n_send, send)
+        dist.all_to_all_single(recv, send, output_split_sizes=[c * width for c in pl["recv_counts"]],
+                               input_split_sizes=[c * width for c in pl["send_counts"]], group=self.group)
+        eng.halo_unpack_by_rank(self._desc, recv, pl["recv_counts_dev"], w, n_recv, n_owned)
+
+    def _run_cuda(self, n_owned: int) -> int:
+        if self.engine is None:
+            raise RuntimeError("halo exchange on GPU buffers needs the b200sph engine (no torch fallback on the product path)")
+        if self._desc is None:
+            self._setup_cuda(n_owned)
+        if self._plan is None or self._plan["n_owned"] != n_owned or not self.reuse_plan:
+            self._build_plan(n_owned)
+            self._move_rows(n_owned)
+        else:
+            # The verdict on the plan is needed before the evaluation starts (an evaluation mutates state -- p, c_s,
+            # S, damage -- so it cannot simply be repeated).  Its 4-byte read-back is queued first and the rows move
+            # speculatively behind it: the host waits for the verdict only, not for the exchange.
+            self._check_plan(n_owned)
+            self._flag_event.record()
+            self._move_rows(n_owned)
+            self._flag_event.synchronize()
+            if int(self._flag_host[0]) != 0:
+                self.stale_plans += 1
+                self._build_plan(n_owned)
+                self._move_rows(n_owned)
+        pl = self._plan
+        self.last = dict(n_halo=pl["n_recv"], sent=pl["n_send"], bytes_sent=pl["n_send"] * self.width * 8, plan_builds=self.plan_builds)
+        return n_owned + pl["n_recv"]
 
     # ------------------------------------------------------------------ CPU tensors (gloo tests): the same rule in torch ops
     def _box_hmax(self, n_owned: int) -> np.ndarray:

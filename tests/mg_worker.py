@@ -114,6 +114,117 @@ def _worker(rank: int, world: int, port: int, config: str, n: int, mode: str, ba
         raise
 
 
+def _plan_worker(rank: int, world: int, port: int, config: str, n: int, result_dir: str):
+    """NCCL only: DistributedRhs with the reusable send plan.  Evaluation 1 builds the plan; before evaluation 2
+    particles deep inside every rank are moved by three times the plan's tolerance, so its check must fail and the
+    plan must be rebuilt before the evaluation runs; evaluation 3 (nothing moved) must reuse the second plan.
+    The owned particles of every evaluation are compared with the single-domain oracle."""
+    import torch
+    import torch.distributed as dist
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.set_num_threads(2)
+        dev = torch.device("cuda", rank % torch.cuda.device_count())
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        sc = scenarios.make(config, n, stirred=True)
+        sw = sc.switches()
+        notes, bad = [], {}
+        with tempfile.TemporaryDirectory() as td:
+            cfg = state.write_material_files(sc, td)
+            mats = api.MaterialTables(config, cfg)
+            full, meta = state.scenario_arrays(sc, mats)
+            meta_run = dict(meta, selfgravity=False)
+            local, n_owned, capacity, mine, dec = multigpu.scatter_scenario(full, sc.n, sc.dim, meta["max_num_flaws"], rank, world)
+            fields = {k: torch.from_numpy(v).to(dev) for k, v in local.items()}
+            eng = api.RhsEngine(config, n_max=capacity, device=dev.index, material_cfg=cfg)
+            eng.set_stream(torch.cuda.current_stream().cuda_stream)
+            drhs = multigpu.DistributedRhs(eng, fields, capacity, n_owned, dec, meta_run, sw)
+
+            def check(label, ref_arrays):
+                ref = {k: v.copy() for k, v in ref_arrays.items()}
+                rc, off, _ = common.oracle_rhs(config, ref, mats, dict(meta_run, n=sc.n))
+                assert rc == 0, (rc, off)
+                out = {k: v.cpu().numpy() for k, v in fields.items()}
+                got_noi = out["noi"].reshape(capacity, -1)[:n_owned, 0]
+                if not np.array_equal(got_noi, ref["noi"][mine]):
+                    bad[label + ":noi"] = int(np.abs(got_noi - ref["noi"][mine]).max())
+                for name in FIELDS:
+                    if name not in out or name not in ref or name.startswith("g_a"):
+                        continue
+                    per = ref[name].size // sc.n
+                    got = out[name].reshape(capacity, per)[:n_owned]
+                    want = ref[name].reshape(sc.n, per)[mine]
+                    scale = float(np.sqrt(np.mean(ref[name].astype(np.float64) ** 2)))
+                    err = common.field_error(got, want, scale)
+                    if not err <= common.RTOL:
+                        bad[f"{label}:{name}"] = err
+
+            drhs.eval()
+            check("eval1", full)
+            assert drhs.halo.plan_builds == 1 and drhs.halo.stale_plans == 0, (drhs.halo.plan_builds, drhs.halo.stale_plans)
+
+            # move particles that are far from every foreign domain (so halo membership cannot change) beyond the tolerance
+            max_move = drhs.halo._plan["max_move"]
+            boxes, box_rank = dec.all_boxes()
+            ax = ["x", "y", "z"][: sc.dim]
+            pos = np.stack([full[a] for a in ax], axis=1)
+            owner = dec.owner_of(dec.cell_ids(pos))
+            hmax = float(full["h"].max())
+            deep = np.ones(sc.n, dtype=bool)
+            for b in range(len(box_rank)):
+                foreign = owner != box_rank[b]
+                gap = np.maximum(np.maximum(boxes[b, : sc.dim] - pos, pos - boxes[b, 3: 3 + sc.dim]), 0.0)
+                deep &= ~(foreign & ((gap * gap).sum(axis=1) < (3.0 * hmax) ** 2))
+            assert deep.sum() > 0, "no particle is deep inside its rank: enlarge the test case"
+            moved = {k: v.copy() for k, v in full.items()}
+            moved["x"][deep] += 3.0 * max_move
+
+            def load_state(src):
+                # the integrator hands every evaluation the state it integrated: (re)load all owned rows
+                for name, arr in src.items():
+                    per = arr.size // sc.n
+                    fields[name].view(capacity, per)[:n_owned] = torch.from_numpy(arr.reshape(sc.n, per)[mine]).to(dev)
+
+            load_state(moved)
+            drhs.eval()
+            check("eval2", moved)
+            assert drhs.halo.plan_builds == 2 and drhs.halo.stale_plans == 1, (drhs.halo.plan_builds, drhs.halo.stale_plans)
+            load_state(moved)
+            drhs.eval()
+            check("eval3", moved)
+            assert drhs.halo.plan_builds == 2 and drhs.halo.stale_plans == 1, (drhs.halo.plan_builds, drhs.halo.stale_plans)
+            notes.append(f"n_owned={n_owned} n_halo={drhs.n_total - n_owned} moved={int(deep[mine].sum())} max_move={max_move:.3e}")
+            eng.close()
+        with open(os.path.join(result_dir, f"rank{rank}.txt"), "w") as fh:
+            fh.write("OK\n" if not bad else f"MISMATCH {bad}\n")
+            fh.write("\n".join(notes) + "\n")
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        with open(os.path.join(result_dir, f"rank{rank}.txt"), "w") as fh:
+            fh.write("EXCEPTION\n" + traceback.format_exc())
+        raise
+
+
+def run_plan(config: str, n: int, world: int) -> list:
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with tempfile.TemporaryDirectory() as rd:
+        try:
+            mp.spawn(_plan_worker, args=(world, port, config, n, rd), nprocs=world, join=True)
+        finally:
+            lines = []
+            for r in range(world):
+                path = os.path.join(rd, f"rank{r}.txt")
+                lines.append(open(path).read() if os.path.exists(path) else "NO RESULT")
+    return lines
+
+
 def run(config: str, n: int, world: int, mode: str, backend: str) -> list:
     """Spawn `world` ranks; returns the per-rank result lines."""
     import socket

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Stage-by-stage wall clock of the GPU halo exchange (diagnosis; run under torchrun with >= 2 GPUs).
-Each stage is bracketed by torch.cuda.synchronize(), so the numbers add up to more than the pipelined cost."""
+"""Wall clock of the GPU halo exchange, deciding every time vs reusing the send plan, and of its stages
+(diagnosis; run under torchrun with >= 2 GPUs).  Back-to-back calls, one synchronisation per measurement."""
 import os, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
@@ -21,41 +21,30 @@ eng = api.RhsEngine(workload, n_max=cap, device=lr, material_cfg=cfg)
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
 dev = {k: torch.from_numpy(v).cuda() for k, v in arrays.items()}
 hx = multigpu.HaloExchange(dev, cap, dec, levels=multigpu.halo_levels(sc.switches()), engine=eng)
-for _ in range(3):
-    hx.run(n)
-torch.cuda.synchronize(); dist.barrier()
 
-def timed(label, fn, acc):
-    torch.cuda.synchronize(); t0 = time.perf_counter(); out = fn(); torch.cuda.synchronize()
-    acc[label] = acc.get(label, 0.0) + (time.perf_counter() - t0) * 1e3
-    return out
+def wall(fn, reps):
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) * 1e3 / reps
 
+hx.run(n)
 acc = {}
-reps = 20
-f = dev
-nb, w = hx._nb_max, world
-for _ in range(reps):
-    dist.barrier()
-    mine = hx._meta_mine
-    timed("box_hmax", lambda: eng.halo_box_hmax(f["x"], f.get("y"), f.get("z"), f["h"], n, mine[:nb]), acc)
-    timed("select", lambda: eng.halo_select(f["x"], f.get("y"), f.get("z"), f["h"], n, hx._hmax_used if hx.levels == 2 else None, nb,
-                                            hx._idx, hx._counts), acc)
-    def share():
-        mine[nb:].copy_(hx._counts)
-        dist.all_gather_into_tensor(hx._meta_all, mine)
-        hx._meta_host.copy_(hx._meta_all, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return hx._meta_host.view(w, nb + w + 1).numpy()
-    table = timed("all_gather_meta+read", share, acc)
-    counts = table[:, nb: nb + w]
-    sc_, rc_ = [int(c) for c in counts[rank]], [int(c) for c in counts[:, rank]]
-    ns, nr = sum(sc_), sum(rc_)
-    send = hx._send[: ns * hx.width].view(ns, hx.width); recv = hx._recv[: nr * hx.width].view(nr, hx.width)
-    timed("pack", lambda: eng.halo_pack(hx._desc, hx._idx, ns, send), acc)
-    timed("a2a_data", lambda: dist.all_to_all_single(recv, send, output_split_sizes=rc_, input_split_sizes=sc_), acc)
-    timed("unpack", lambda: eng.halo_unpack(hx._desc, recv, nr, n), acc)
-    dist.barrier()
-    t0 = time.perf_counter(); hx.run(n); torch.cuda.synchronize(); acc["whole_run"] = acc.get("whole_run", 0.0) + (time.perf_counter() - t0) * 1e3
+hx.reuse_plan = False
+acc["decide_every_time"] = wall(lambda: hx.run(n), 20)
+hx.reuse_plan = True
+hx.run(n)
+acc["reuse_plan"] = wall(lambda: hx.run(n), 20)
+pl = hx._plan
+w = world
+send = hx._send[: pl["n_send"] * hx.width]; recv = hx._recv[: pl["n_recv"] * hx.width]
+acc["check"] = wall(lambda: hx._check_plan(n), 20)
+acc["pack"] = wall(lambda: eng.halo_pack_by_rank(hx._desc, hx._idx, pl["send_counts_dev"], w, pl["n_send"], send), 20)
+acc["a2a_data"] = wall(lambda: dist.all_to_all_single(recv, send, output_split_sizes=[c * hx.width for c in pl["recv_counts"]],
+                                                      input_split_sizes=[c * hx.width for c in pl["send_counts"]]), 20)
+acc["unpack"] = wall(lambda: eng.halo_unpack_by_rank(hx._desc, recv, pl["recv_counts_dev"], w, pl["n_recv"], n), 20)
 if rank == 0:
-    print({k: round(v / reps, 4) for k, v in acc.items()}, "n_send", ns, "width", hx.width, "boxes", len(hx.box_rank), "retry", hx.last_retry, flush=True)
+    print({k: round(v, 4) for k, v in acc.items()}, "ms; n_send", pl["n_send"], "width", hx.width, "boxes", len(hx.box_rank),
+          "plan_builds", hx.plan_builds, flush=True)
 dist.destroy_process_group()
