@@ -124,7 +124,7 @@ extern "C" int b200sph_create(b200sph_handle **out, int n_max, int device, uint6
         return B200SPH_ERR_CUDA;
     }
     if (gravity_tree_create(h) != 0) {
-        snprintf(g_create_error, sizeof(g_create_error), "gravity tree allocation failed: %s", h->err);
+        snprintf(g_create_error, sizeof(g_create_error), "gravity tree allocation failed: %.400s", h->err);
         b200sph_destroy(h);
         return B200SPH_ERR_CUDA;
     }

@@ -886,6 +886,7 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
     const int matId = s.mat[k];
     const b200sph_particle_arrays &p = v.p;
     const b200sph_particle_arrays &pr = v.p_rhs;
+    (void)pr;   /* only the solid switch sets write p_rhs scratch here */
     const double m = s.vel4[k].w;
     double rho = use_rho_sorted ? rho_sorted[k] : p.rho[i];
 
@@ -1217,6 +1218,7 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
     const int matId = s.mat[k];
     const b200sph_particle_arrays &p = v.p;
     const b200sph_particle_arrays &pr = v.p_rhs;
+    (void)pr;
     if (i >= s.n_owned) return;   /* halo copy: its owner computes the rates */
     const Rec4 pi = ld_rec(&s.pos4[k]);
     const Rec4 vi = ld_rec(&s.vel4[k]);
