@@ -1028,7 +1028,8 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
     double ten[4 * TEN_RECS];
 #pragma unroll
     for (int c = 0; c < 4 * TEN_RECS; c++) ten[c] = 0.0;
-    double sigma[DIM][DIM];
+    double sigma[DIM][DIM];   /* kept in registers for the artificial-stress eigen-decomposition below */
+    (void)sigma;
 #pragma unroll
     for (int a = 0; a < DIM; a++)
 #pragma unroll
