@@ -1028,8 +1028,9 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
     double ten[4 * TEN_RECS];
 #pragma unroll
     for (int c = 0; c < 4 * TEN_RECS; c++) ten[c] = 0.0;
-    double sigma[DIM][DIM];   /* kept in registers for the artificial-stress eigen-decomposition below */
-    (void)sigma;
+#if ARTIFICIAL_STRESS
+    double sigma[DIM][DIM];   /* kept in registers for the eigen-decomposition below */
+#endif
 #pragma unroll
     for (int a = 0; a < DIM; a++)
 #pragma unroll
@@ -1040,7 +1041,9 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
             double sg = S[a][b];
 #endif
             if (a == b) sg -= ptmp;
+#if ARTIFICIAL_STRESS
             sigma[a][b] = sg;
+#endif
             pr.sigma[(size_t)i * DD + a * DIM + b] = sg;
             ten[ten_sig(a, b)] = sg * irho2;
         }
