@@ -79,6 +79,16 @@ constexpr int kPairUnroll = B200_PAIR_UNROLL;
 #else
 #define PAIR_UNROLL   /* no pragma at all: "#pragma unroll 1" would change the code the compiler emits today */
 #endif
+/* Round-2 experiment knobs of the neighbour search (defaults = the code measured in round 1; DESIGN.md section 3,
+ * "Where the stall samples sit"): candidates fetched per loop trip, and fetching the next row's cell_start pair
+ * while the current row is scanned. */
+#ifndef B200_SEARCH_UNROLL
+#define B200_SEARCH_UNROLL 4
+#endif
+#ifndef B200_SEARCH_ROW_PREFETCH
+#define B200_SEARCH_ROW_PREFETCH 0
+#endif
+constexpr int kSearchUnroll = B200_SEARCH_UNROLL;
 #ifndef B200_CELL_DIV
 #define B200_CELL_DIV 2.0
 #endif
@@ -498,6 +508,32 @@ __device__ __forceinline__ bool search_hit(const float4 &si, float thr_i, const 
     return dd < fminf(thr_i, c.w);
 }
 
+#if B200_SEARCH_ROW_PREFETCH
+/* first and one-past-last sorted slot of the candidates of row (y, z) for particle pi, clipped to the sphere;
+ * an empty range when the row cannot hold a neighbour */
+__device__ __forceinline__ void search_row_range(const Sorted &s, const Domain &d, const Stencil &st, const Rec4 &pi, double reach2,
+                                                 double slack, int y, int z, int &jb, int &je)
+{
+    jb = 0; je = 0;
+    double rem = reach2;
+#if DIM > 2
+    const double gz = row_gap(pi.z, d.lo[2], d.cell, z, d.nc[2], slack);
+    rem -= gz * gz;
+#endif
+#if DIM > 1
+    const double gy = row_gap(pi.y, d.lo[1], d.cell, y, d.nc[1], slack);
+    rem -= gy * gy;
+#endif
+    if (rem <= 0.0) return;
+    const double w = (double)__fsqrt_ru(__double2float_ru(rem)) * (1.0 + 1e-6) + slack;
+    const int xa = max(st.x0, cell_coord(pi.x - w, d.lo[0], d.cell_inv, d.nc[0]));
+    const int xb = min(st.x1, cell_coord(pi.x + w, d.lo[0], d.cell_inv, d.nc[0]));
+    const int row = d.nc[0] * (y + d.nc[1] * z);
+    jb = s.cell_start[row + xa];
+    je = s.cell_start[row + xb + 1];
+}
+#endif
+
 __global__ void __launch_bounds__(128)
 k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloDomains *hd, int halo_sums)
 {
@@ -527,6 +563,38 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloD
     int *const base = s.nbr + NBR_SLOT(k, 0);
     const double reach2 = __dmul_rn(pi.w, pi.w) * (1.0 + 1e-9);
     const double slack = 1e-9 * d.cell;
+#if B200_SEARCH_ROW_PREFETCH
+    {
+        /* rows flattened; the cell_start pair of row r + 1 is requested before the candidates of row r are scanned */
+        const int ny = st.y1 - st.y0 + 1, nrows = ny * (st.z1 - st.z0 + 1);
+        int jb_next, je_next;
+        search_row_range(s, d, st, pi, reach2, slack, st.y0, st.z0, jb_next, je_next);
+        for (int r = 0; r < nrows; r++) {
+            const int jb = jb_next, je = je_next;
+            if (r + 1 < nrows) {
+                const int zr = (r + 1) / ny;
+                search_row_range(s, d, st, pi, reach2, slack, st.y0 + (r + 1) - zr * ny, st.z0 + zr, jb_next, je_next);
+            }
+            if (cnt + (je - jb) <= MAX_NUM_INTERACTIONS) {
+                int *slot = base + cnt * NBR_TILE;
+#pragma unroll kSearchUnroll
+                for (int j = jb; j < je; j++) {
+                    const bool hit = search_hit(si, thr_i, __ldg(&s.srch[j]));
+                    if (hit) *slot = j;
+                    slot += hit ? NBR_TILE : 0;
+                    cnt += hit ? 1 : 0;
+                }
+            } else {
+                for (int j = jb; j < je; j++) {
+                    if (search_hit(si, thr_i, __ldg(&s.srch[j]))) {
+                        if (cnt < MAX_NUM_INTERACTIONS) base[cnt * NBR_TILE] = j;
+                        cnt++;
+                    }
+                }
+            }
+        }
+    }
+#else
     for (int z = st.z0; z <= st.z1; z++) {
 #if DIM > 2
         const double gz = row_gap(pi.z, d.lo[2], d.cell, z, d.nc[2], slack);
@@ -552,7 +620,7 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloD
             if (cnt + (je - jb) <= MAX_NUM_INTERACTIONS) {
                 /* the whole row fits: no overflow check per candidate */
                 int *slot = base + cnt * NBR_TILE;
-#pragma unroll 4
+#pragma unroll kSearchUnroll
                 for (int j = jb; j < je; j++) {
                     const bool hit = search_hit(si, thr_i, __ldg(&s.srch[j]));
                     if (hit) *slot = j;   /* predicated store, no divergent branch */
@@ -569,6 +637,7 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloD
             }
         }
     }
+#endif
     if (cnt > MAX_NUM_INTERACTIONS) {
         /* more survivors than list slots: decide with the exact test (the reference asserts on the exact count) */
         cnt = neighbours_exact(s, d, k, pi, st);

@@ -69,10 +69,30 @@ __device__ __forceinline__ double kernel_norm(double hinv)
 #ifndef B200_RSQRT_OPAQUE
 #define B200_RSQRT_OPAQUE SOLID
 #endif
+/* Round-2 experiment knob (default off): reciprocal square root seeded by the FP32 MUFU and finished with two
+ * FP64 Newton steps (about 2 ulp), without the range check of rsqrt(double) -- rsqrt is 20 % of the instructions
+ * of the hydro force loop.  Arguments outside the FP32 range take the library routine. */
+#ifndef B200_FAST_RSQRT
+#define B200_FAST_RSQRT 0
+#endif
+__device__ __forceinline__ double pair_rsqrt(double x)
+{
+#if B200_FAST_RSQRT
+    if (x > 1e-30 && x < 1e30) {
+        double y = (double)rsqrtf(__double2float_rn(x));
+        const double hx = 0.5 * x;
+        y = y * fma(-hx * y, y, 1.5);
+        y = y * fma(-hx * y, y, 1.5);
+        return y;
+    }
+#endif
+    return rsqrt(x);
+}
+
 __device__ __forceinline__ void cubic_spline(double r2, double hinv, double &W, double &g)
 {
     const double f = kernel_norm(hinv);
-    double rinv = rsqrt(r2);
+    double rinv = pair_rsqrt(r2);
     /* opaque to the optimiser: nvcc otherwise re-evaluates the reciprocal square root (MUFU + 5 FP64
      * instructions + slow-path check) in each branch below instead of keeping it in a register */
 #if B200_RSQRT_OPAQUE
