@@ -346,8 +346,8 @@ class HaloExchange:
         table = flat.view(self.world, nb_max).numpy()
         return np.concatenate([table[r, : self.box_counts[r]] for r in range(self.world)])
 
-    def _needed_by(self, n_owned: int, extra: np.ndarray) -> torch.Tensor:
-        """int64 mask per owned particle: bit r set <=> rank r needs a copy."""
+    def _needed_by(self, n_owned: int, extra: np.ndarray, reach_scale: float = 1.0, skin: float = 0.0) -> torch.Tensor:
+        """int64 mask per owned particle: bit r set <=> rank r needs a copy (same rule as h_mask in csrc/halo.cu)."""
         f = self.fields
         pos = torch.stack([f[a][:n_owned] for a in self.axes], dim=1)
         h = f["h"][:n_owned]
@@ -359,7 +359,7 @@ class HaloExchange:
             lo = torch.as_tensor(self.boxes[b, : self.dim])
             hi = torch.as_tensor(self.boxes[b, 3: 3 + self.dim])
             gap = torch.clamp(torch.maximum(lo - pos, pos - hi), min=0.0)
-            reach = (h + float(extra[b])) * (1.0 + 1e-9)
+            reach = (h + float(extra[b])) * reach_scale * (1.0 + 1e-9) + skin
             mask |= ((gap * gap).sum(dim=1) < reach * reach).to(torch.int64) << r
         return mask
 
@@ -372,19 +372,23 @@ class HaloExchange:
             return n_owned
         if dev.type == "cuda":
             return self._run_cuda(n_owned)
+        return self.move_cpu(n_owned, self.select_cpu(n_owned))
+
+    def select_cpu(self, n_owned: int, reach_scale: float = 1.0, skin: float = 0.0) -> list:
+        """CPU tensors: per destination rank, the ascending indices of the owned particles it needs (empty for this rank).
+        With reach_scale = 1 + growth and skin = 2 D this is the decision a reusable plan is built from."""
         # second halo level: a copy must also be complete around its own neighbours, which reach up to the
         # largest smoothing length found in the owner's box it borders (all-gathered per box)
         extra = self._box_hmax(n_owned) if self.levels == 2 else np.zeros(len(self.box_rank))
-        mask = self._needed_by(n_owned, extra)
+        mask = self._needed_by(n_owned, extra, reach_scale, skin)
+        empty = torch.empty(0, dtype=torch.int64)
+        return [empty if r == self.rank else torch.nonzero((mask >> r) & 1, as_tuple=False).flatten() for r in range(self.world)]
 
-        send_idx, send_counts = [], []
-        for r in range(self.world):
-            if r == self.rank:
-                send_counts.append(0)
-                continue
-            idx = torch.nonzero((mask >> r) & 1, as_tuple=False).flatten()
-            send_idx.append(idx)
-            send_counts.append(int(idx.numel()))
+    def move_cpu(self, n_owned: int, send_idx: list) -> int:
+        """CPU tensors: send the CURRENT state of the listed particles and append what arrives behind the owned rows."""
+        f = self.fields
+        dev = f["x"].device
+        send_counts = [int(idx.numel()) for idx in send_idx]
         sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
         rc = torch.empty_like(sc)
         dist.all_to_all_single(rc, sc, group=self.group)

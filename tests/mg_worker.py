@@ -45,8 +45,38 @@ def _worker(rank: int, world: int, port: int, config: str, n: int, mode: str, ba
             gravity = bool(meta["selfgravity"]) and use_cuda      # the oracle has no notion of foreign gravity sources
             meta_run = dict(meta, selfgravity=gravity)
 
+            # mode "oracle_plan": the halo decision is taken at the scenario's positions with the head-room of a
+            # reusable plan (reach * (1 + growth) + 2 D), THEN every particle moves by up to D and h grows by up to
+            # `growth`; the old decision must still hand every rank all it needs for the moved state.
+            moved = None
+            if mode == "oracle_plan":
+                rng = np.random.default_rng(424242)
+                h_evolves = bool(sw.get("VARIABLE_SML", 0) or sw.get("INTEGRATE_SML", 0))
+                growth = multigpu.HaloExchange.H_GROWTH if h_evolves else 0.0
+                max_move = multigpu.HaloExchange.SKIN * float(full["h"].min())
+                # adversarial motion: every particle heads for the nearest foreign domain (pairs across a cut approach
+                # each other by almost 2 D); particles that touch a foreign box move in a random direction
+                pos0 = np.stack([full[a] for a in ["x", "y", "z"][: sc.dim]], axis=1)
+                dec0, _ = multigpu.morton_partition(pos0, world)
+                boxes0, box_rank0 = dec0.all_boxes()
+                owner0 = dec0.owner_of(dec0.cell_ids(pos0))
+                direction = rng.normal(size=(sc.n, sc.dim))
+                best = np.full(sc.n, np.inf)
+                for b in range(len(box_rank0)):
+                    vec = np.maximum(boxes0[b, : sc.dim] - pos0, 0.0) - np.maximum(pos0 - boxes0[b, 3: 3 + sc.dim], 0.0)
+                    d2 = (vec * vec).sum(axis=1)
+                    better = (owner0 != box_rank0[b]) & (d2 < best) & (d2 > 0.0)
+                    direction[better] = vec[better]
+                    best[better] = d2[better]
+                direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+                step = direction * (0.999 * max_move)
+                moved = {k: v.copy() for k, v in full.items()}
+                for a, name in enumerate(["x", "y", "z"][: sc.dim]):
+                    moved[name] += step[:, a]
+                moved["h"] *= 1.0 + 0.999 * growth * rng.random(sc.n)
+
             # single-domain answer
-            ref = {k: v.copy() for k, v in full.items()}
+            ref = {k: v.copy() for k, v in (moved if moved is not None else full).items()}
             rc, off, _ = common.oracle_rhs(config, ref, mats, dict(meta_run, n=sc.n))
             assert rc == 0, (rc, off)
 
@@ -57,7 +87,13 @@ def _worker(rank: int, world: int, port: int, config: str, n: int, mode: str, ba
             if eng is not None:
                 eng.set_stream(torch.cuda.current_stream().cuda_stream)   # library kernels ordered with torch / NCCL work
             halo = multigpu.HaloExchange(fields, capacity, dec, levels=multigpu.halo_levels(sw), engine=eng)
-            n_total = halo.run(n_owned)
+            if moved is None:
+                n_total = halo.run(n_owned)
+            else:
+                send_idx = halo.select_cpu(n_owned, 1.0 + growth, 2.0 * max_move)      # decided before anything moved
+                for name in ["x", "y", "z"][: sc.dim] + ["h"]:
+                    fields[name][:n_owned] = torch.from_numpy(moved[name][mine])
+                n_total = halo.move_cpu(n_owned, send_idx)                             # current state of the old selection
             assert n_total > n_owned, "a rank without halo particles means the decomposition is not being exercised"
 
             if use_cuda:

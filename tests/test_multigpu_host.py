@@ -16,6 +16,16 @@ def test_ranks_match_single_domain(config, n, world):
     assert all(line.startswith("OK") for line in lines), lines
 
 
+@pytest.mark.parametrize("config,n,world", [("sedov", 12000, 2), ("impact", 8000, 2), ("rings", 8000, 3), ("giant_hydro", 8000, 2)])
+def test_plan_decision_survives_motion_within_its_tolerance(config, n, world):
+    """The rule a reusable send plan is built from -- reach (h_k + h_max(box)) (1 + growth) + 2 D -- decided at the
+    initial positions must still be complete after every particle moved by D TOWARDS the nearest foreign domain and h
+    grew by up to `growth`: the oracle on owned + halo of the MOVED state reproduces the single-domain result of the
+    moved state.  (The same motion breaks a decision taken without the head-room: neighbour counts differ.)"""
+    lines = mg_worker.run(config, n, world, "oracle_plan", "gloo")
+    assert all(line.startswith("OK") for line in lines), lines
+
+
 def test_morton_partition_is_a_partition():
     rng = np.random.default_rng(5)
     x = rng.random((50000, 3))
