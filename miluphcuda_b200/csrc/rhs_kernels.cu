@@ -721,6 +721,18 @@ struct PairRecs {
 #endif
 };
 
+/* B200_PREFETCH_TENSORS_L1 (round-2 experiment knob, default off): the solid force loop prefetches positions,
+ * velocities and gas records one pair ahead in registers but has none left (168) for the three tensor records,
+ * whose load is then waited for in the iteration that issued it -- 34 % of the stall samples.
+ * prefetch.global.L1 needs no register: the next neighbour's tensor lines are requested one iteration early. */
+#ifndef B200_PREFETCH_TENSORS_L1
+#define B200_PREFETCH_TENSORS_L1 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *ptr)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
+
 /* B200_PREFETCH_TENSORS: also fetch the solid tensor records one iteration ahead (costs 8*TEN_RECS registers) */
 #ifndef B200_PREFETCH_TENSORS
 #define B200_PREFETCH_TENSORS 0
@@ -1375,6 +1387,11 @@ PAIR_UNROLL
             j_next = j_next2;
             j_next2 = s.nbr[NBR_SLOT(k, min(q + 2, nslots - 1))];
             load_force_recs(s, j_next, nxt);   /* past the end this re-reads the last neighbour (harmless) */
+#if SOLID && B200_PREFETCH_TENSORS_L1
+            /* the NEXT neighbour's tensor records, requested into L1 without a destination register */
+            prefetch_l1(&s.ten[(size_t)j_next * TEN_RECS]);
+            prefetch_l1(&s.ten[(size_t)j_next * TEN_RECS + (TEN_RECS - 1)]);
+#endif
             const Rec4 &pj = cur.p;
             double dr[3], dv[3], W, g;
             const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
