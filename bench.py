@@ -5,7 +5,15 @@ One "step" = one evaluation of the hot path (what miluphcuda's rightHandSide() d
 reference src/rhs.cu:143-861) over every particle of a synthetic scenario; the metric
 is RHS evaluations x particles / second (BASELINE.json).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sedov] [--particles 1000000]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload impact] [--particles 1000000] [--state evolved|step0]
+
+Default workload: the 10^6-particle solid impact per GPU (BASELINE.json: the >= 5x target is defined on it; 16M on 8
+GPUs = 2M per GPU with --particles 2000000).  Default state on one GPU: EVOLVED -- the scenario after >= 20 accepted
+rk2_adaptive steps (SURVEY 8d's second measurement point), not the pristine step-0 lattice (zero velocities, zero
+stress, no active flaws).  The evolved input is prepared, before anything is timed, by the reference's own integrator
+(oracle/_ref/miluphcuda_<workload> with REF_EVOLVE: the same state the reference arm times); the step-0 state is
+measured as well and reported under "step0".  Without that binary, and on several GPUs (the reference is single-GPU
+and cannot evolve a 16M-particle set), the step-0 state is the timed one and `config.state` says so.
   python bench.py --impl reference ...      # the reference's own implementation, same metric/config
 
 Arms
@@ -35,7 +43,7 @@ sys.path.insert(0, REPO)
 METRIC = "sph_particle_updates_per_s"
 UNIT = "particle-updates/s"
 DEFAULT_PARTICLES = {"shocktube": 10000, "sedov": 1000000, "rings": 1000000, "impact": 1000000,
-                     "giant_hydro": 1000000, "giant_solid": 1000000}
+                     "giant_hydro": 1000000, "giant_solid": 1000000, "nakamura": 1000000}
 
 
 # ----------------------------------------------------------------------------- roofline constants
@@ -112,6 +120,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_label(workload: str, n_global: int, n_per_gpu: int, state: str, accepted) -> str:
+    """Identical for both arms when they ran the same particle set in the same state."""
+    what = (f"evolved: after {accepted} accepted rk2_adaptive steps of the reference integrator" if state == "evolved"
+            else "step-0 state")
+    return f"{workload} (synthetic, {n_global} particles, {what})"
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference_arm(args, rank: int, world: int) -> None:
     if rank != 0:
@@ -124,10 +139,13 @@ def run_reference_arm(args, rank: int, world: int) -> None:
             "config": {"workload": f"{workload} (synthetic, {n} particles requested)", "particles": n}}
     if os.path.exists(binary):
         import make_golden
-        res = make_golden.time_reference(workload, n, calls=args.steps, warmup=args.warmup)
+        evolve = (args.state or "evolved") == "evolved"
+        res = make_golden.time_reference(workload, n, calls=args.steps, warmup=args.warmup, evolve=evolve)
         value = res["updates_per_s"]
         base["config"]["particles"] = res["n"]
-        base["config"]["workload"] = f"{workload} (synthetic, {res['n']} particles)"
+        base["config"]["workload"] = workload_label(workload, res["n"], res["n"], "evolved" if evolve else "step0",
+                                                    (res.get("evolved_steps") or {}).get("accepted"))
+        base["config"]["state"] = "evolved" if evolve else "step0"
         base.update({"value": value, "ms_per_step": res["ms_per_call"],
                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                                       "sample": ("miluphcuda has no CPU path: the UNMODIFIED reference CUDA build (sm_100a, quiet debug flags) "
@@ -177,7 +195,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="sedov", choices=list(DEFAULT_PARTICLES))
+    ap.add_argument("--workload", default="impact", choices=list(DEFAULT_PARTICLES))
+    ap.add_argument("--state", default=None, choices=["evolved", "step0"], help="default: evolved on one GPU, step0 on several")
     ap.add_argument("--particles", type=int, default=None, help="particles per GPU (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -215,17 +234,28 @@ def main() -> None:
     tmp = tempfile.TemporaryDirectory()
     cfg = state.write_material_files(sc, tmp.name)
     mats = api.MaterialTables(workload, cfg)
-    full, meta = state.scenario_arrays(sc, mats)
-    arrays, n, capacity, _, dec = multigpu.scatter_scenario(full, sc.n, sc.dim, meta["max_num_flaws"], rank, world)
+    full_step0, meta = state.scenario_arrays(sc, mats)
     n_global = sc.n
-    del full
-    eng = api.RhsEngine(workload, n_max=capacity, device=local_rank, material_cfg=cfg)
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
 
-    dev = {k: torch.from_numpy(v).cuda() for k, v in arrays.items()}
-    drhs = multigpu.DistributedRhs(eng, dev, capacity, n, dec, meta, sc.switches())
+    # ---- input preparation (untimed): the evolved state, made by the reference's own integrator (see module docstring)
+    state_kind = args.state or ("evolved" if world == 1 else "step0")
+    state_note, evolved_steps, full_evolved = None, None, None
+    if state_kind == "evolved":
+        binary = os.path.join(REPO, "oracle", "_ref", f"miluphcuda_{workload}")
+        if world > 1:
+            state_kind, state_note = "step0", "the reference integrator that prepares the evolved state is single-GPU"
+        elif not os.path.exists(binary):
+            state_kind, state_note = "step0", f"{os.path.relpath(binary, REPO)} is not built: no integrator to evolve the state with"
+        else:
+            sys.path.insert(0, os.path.join(REPO, "oracle"))
+            import make_golden
+            d_in, evolved_steps = make_golden.evolved_state(sc, tmp.name)
+            full_evolved, _ = make_golden.arrays_from_dump(workload, d_in, bool(sc.selfgravity))
+            del d_in
+
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 512 MiB > 126 MB L2
+    stream = torch.cuda.current_stream()
+    engines = {}
 
     def barrier():
         torch.cuda.synchronize()
@@ -233,44 +263,67 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        drhs.eval()
-    barrier()
+    def measure(full, steps, with_clocks):
+        """Warm-up + exactly `steps` timed evaluations of one particle set; device times by CUDA events, max over ranks."""
+        arrays, n, capacity, _, dec = multigpu.scatter_scenario(full, sc.n, sc.dim, meta["max_num_flaws"], rank, world)
+        if capacity not in engines:
+            engines[capacity] = api.RhsEngine(workload, n_max=capacity, device=local_rank, material_cfg=cfg)
+            engines[capacity].set_stream(stream.cuda_stream)
+        eng = engines[capacity]
+        dev = {k: torch.from_numpy(v).cuda() for k, v in arrays.items()}
+        drhs = multigpu.DistributedRhs(eng, dev, capacity, n, dec, meta, sc.switches())
+        for _ in range(args.warmup):
+            drhs.eval()
+        barrier()
+        sampler = ClockSampler(local_rank) if with_clocks else None
+        if sampler:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(steps)]
+        stage_ms, launches = {}, 0
+        t_wall0 = time.time()
+        for k in range(steps):
+            flush.fill_(float(k))           # evict L2 between timed steps (not timed)
+            ev[k][0].record(stream)
+            drhs.exchange()                 # halo exchange (+ gravity sources) over NCCL; a no-op on one GPU
+            ev[k][2].record(stream)
+            drhs.compute()                  # b200sph_rhs_eval on owned + halo particles
+            ev[k][1].record(stream)
+            st = eng.stats()
+            launches += st["kernel_launches"]
+            for key, val in st.items():
+                if key.startswith("ms_"):
+                    stage_ms[key] = stage_ms.get(key, 0.0) + val
+        barrier()
+        t_wall = time.time() - t_wall0
+        clocks = sampler.stop() if sampler else None
+        dev_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
+        exch_ms = sum(a.elapsed_time(c) for a, _, c in ev)
+        # max over ranks of the device time for exactly K steps
+        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        cnt = torch.tensor([float(n)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        return dict(arrays=arrays, n=n, capacity=capacity, dec=dec, eng=eng, dev=dev, drhs=drhs, stage_ms=stage_ms, launches=launches,
+                    t_wall=t_wall, clocks=clocks, exch_ms=exch_ms, total_ms=float(t.item()), total_particles=float(cnt.item()),
+                    stats=eng.stats())
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    stage_ms = {}
-    launches = 0
-    t_wall0 = time.time()
-    for k in range(args.steps):
-        flush.fill_(float(k))           # evict L2 between timed steps (not timed)
-        ev[k][0].record(stream)
-        drhs.exchange()                 # halo exchange (+ gravity sources) over NCCL; a no-op on one GPU
-        ev[k][2].record(stream)
-        drhs.compute()                  # b200sph_rhs_eval on owned + halo particles
-        ev[k][1].record(stream)
-        st = eng.stats()
-        launches += st["kernel_launches"]
-        for key, val in st.items():
-            if key.startswith("ms_"):
-                stage_ms[key] = stage_ms.get(key, 0.0) + val
-    barrier()
-    t_wall = time.time() - t_wall0
-    clocks = sampler.stop()
-    dev_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
-    exch_ms = sum(a.elapsed_time(c) for a, _, c in ev)
-    stats = eng.stats()
-
-    # max over ranks of the device time for exactly K steps
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(n)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    total_ms = float(t.item())
-    total_particles = float(cnt.item())
+    step0 = None
+    if full_evolved is not None:
+        # second measurement point of SURVEY 8d: the pristine step-0 state, reported next to the headline
+        m0 = measure(full_step0, max(3, min(args.steps, 10)), with_clocks=False)
+        steps0 = max(3, min(args.steps, 10))
+        step0 = {"value": m0["total_particles"] * steps0 / (m0["total_ms"] * 1e-3), "unit": UNIT, "ms_per_step": m0["total_ms"] / steps0,
+                 "steps": steps0, "mean_interactions": float(m0["dev"]["noi"][: m0["n"]].sum().item()) / m0["n"],
+                 "stage_ms_per_step": {k: v / steps0 for k, v in m0["stage_ms"].items()}}
+        del m0
+        torch.cuda.empty_cache()
+    M = measure(full_evolved if full_evolved is not None else full_step0, args.steps, with_clocks=True)
+    del full_step0, full_evolved
+    arrays, n, capacity, eng, dev, drhs = M["arrays"], M["n"], M["capacity"], M["eng"], M["dev"], M["drhs"]
+    stage_ms, launches, t_wall, clocks, exch_ms = M["stage_ms"], M["launches"], M["t_wall"], M["clocks"], M["exch_ms"]
+    total_ms, total_particles, stats = M["total_ms"], M["total_particles"], M["stats"]
     # per-rank picture (owned, halo, ms in b200sph_rhs_eval, ms in the exchange incl. waiting for peers): shows imbalance
     mine = torch.tensor([float(n), float(drhs.n_total - n), stage_ms.get("ms_total", 0.0) / args.steps, exch_ms / args.steps],
                         dtype=torch.float64, device="cuda")
@@ -376,7 +429,8 @@ def main() -> None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{workload} (synthetic, {n_global} particles = {n_global // world} per GPU)", "particles": int(total_particles),
+        "config": {"workload": workload_label(workload, n_global, n_global // world, state_kind, evolved_steps),
+                   "state": state_kind, "state_note": state_note, "particles_per_gpu": n_global // world, "particles": int(total_particles),
                    "mean_interactions": total_noi / n, "l2": "512 MiB buffer written between timed steps (untimed)",
                    "timing": "per-step CUDA events on the launching stream, summed over K steps, max over ranks",
                    "multi_gpu": ("Morton-curve domain decomposition, %d-level halo exchange per evaluation (NCCL all_to_all of the "
@@ -388,7 +442,7 @@ def main() -> None:
                    "rank0": {"owned": n, "halo": drhs.n_total - n, "halo_bytes_sent": drhs.halo.last.get("bytes_sent", 0),
                              "exchange_ms_per_step": exch_ms / args.steps},
                    "ranks": {"columns": ["owned", "halo", "rhs_ms", "exchange_ms"], "rows": per_rank}},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "step0": step0,
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "search_grid": {"cells": stats["n_cells"], "cell_size": stats["cell_size"], "max_interactions": stats["max_noi"]},
     }

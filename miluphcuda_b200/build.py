@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-CONFIGS = ("shocktube", "sedov", "rings", "impact", "giant_hydro", "giant_solid")
+CONFIGS = ("shocktube", "sedov", "rings", "impact", "giant_hydro", "giant_solid", "nakamura")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CU_SOURCES = ("libb200sph.cu",)
 C_SOURCES = ("materials.c", "libconfig_lite.c")

@@ -940,6 +940,21 @@ __device__ inline double eos_pressure(const MatParams &M, double rho, double e, 
                            k * (M.pj_alpha_t - 1.0) * M.pj_n2 * (pow(p_s - pr, M.pj_n2 - 1.0) / pow(p_s - p_e, M.pj_n2));
                 else if (pr >= p_t && pr < p_s)
                     dadp = -k * (M.pj_alpha_t - 1.0) * M.pj_n2 * (pow(p_s - pr, M.pj_n2 - 1.0) / pow(p_s - p_e, M.pj_n2));
+            } else if (M.crushcurve_style == 2) {
+                /* experimental crush curve of Blum et al. 2023 with the reference's built-in constants
+                 * (src/pressure.cu:386-410): alpha = (P0/p)^(1/x + b p/x) + 1/phi_max */
+                const double P0 = 0.044e6, x = 8.915, bb = 7e-4 * 1e-6;
+                if (pr > 1.0) {
+                    const double ex = 1.0 / x + bb / x * pr;
+                    dadp = pow(P0 / pr, ex) * (bb / x * log(P0 / pr) - P0 * ex / (P0 * pr));
+                }
+            } else if (M.crushcurve_style == 3) {
+                /* Malamud 2023 (src/pressure.cu:411-423) */
+                if (pr > 1e2) dadp = -0.19341714781149988 / (-pr * sq(0.084 * log(pr) - 0.14736544595161893));
+            } else if (M.crushcurve_style == 4) {
+                /* Malamud 2023, blue curve of their figure 2c: VFF = 0.41 p^0.09, p in MPa (src/pressure.cu:424-440) */
+                const double p_el = 1e6 * pow(1.0 / (0.41 * a0), 1.0 / 0.09);
+                if (pr > p_el) dadp = -0.7611296717250695 * pow(pr, -1.09);
             }
             po.dalphadp = dadp;
             po.dalphadrho = ((pr / (rho * rho) * po.delpdele + al * po.delpdelrho) * dadp) / (al + dadp * (pr - rho * po.delpdelrho));

@@ -22,7 +22,10 @@ from dataclasses import dataclass, field
 import numpy as np
 
 CONFIG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs")
-CONFIG_NAMES = ("shocktube", "sedov", "rings", "impact", "giant_hydro", "giant_solid")
+CONFIG_NAMES = ("shocktube", "sedov", "rings", "impact", "giant_hydro", "giant_solid", "nakamura")
+# scenario variants that run on another config's switch set (library)
+VARIANT_CONFIG = {"giant_aneos": "giant_hydro", "sedov_ignore": "sedov", "impact_ignore": "impact", "giant_ignore": "giant_hydro",
+                  "impact_crush1": "impact", "impact_crush2": "impact", "impact_crush3": "impact", "impact_crush4": "impact"}
 
 
 def read_switches(config: str) -> dict:
@@ -93,6 +96,21 @@ class Scenario:
         sw = self.switches()
         cols = self.columns()
         n = self.n
+        try:
+            # C++ writer: shortest round-trip decimal per double, seconds instead of minutes at 10^6 particles.
+            # Unused flaw slots are nulls -> empty fields, i.e. runs of blanks the reference's fscanf reader skips.
+            import pyarrow as pa
+            import pyarrow.csv as pacsv
+            arrs = [pa.array(np.ascontiguousarray(c)) for c in cols]
+            if sw.get("FRAGMENTATION", 0):
+                nf = np.asarray(self.num_flaws)
+                for f in range(int(nf.max()) if n else 0):
+                    arrs.append(pa.array(np.ascontiguousarray(self.flaws[:, f]), mask=(nf <= f)))
+            table = pa.table(arrs, names=[f"c{k}" for k in range(len(arrs))])
+            pacsv.write_csv(table, path, write_options=pacsv.WriteOptions(include_header=False, delimiter=" ", quoting_style="none"))
+            return
+        except ImportError:
+            pass
         fixed = []
         for c in cols:
             c = np.asarray(c)
@@ -349,6 +367,95 @@ def impact(n_target: int = 58402, seed: int = 20240229) -> Scenario:
     )
 
 
+# ---------------------------------------------------------------- nakamura (von Mises + Grady-Kipp on S)
+_NAKAMURA_CFG = """materials = (
+  {{
+    ID = 0;
+    name = "Basalt Nakamura (Tillotson)";
+    sml = {sml:.17e};
+    artificial_viscosity = {{ alpha = 1.0; beta = 2.0; }};
+    eos = {{
+      type = 2
+      shear_modulus = 22.7e9
+      bulk_modulus = 26.7e9
+      yield_stress = 3.5e9
+      till_rho_0 = 2.7e3
+      till_A = 26.7e9
+      till_B = 26.7e9
+      till_E_0 = 487e6
+      till_E_iv = 4.72e6
+      till_E_cv = 18.2e6
+      till_a = 0.5
+      till_b = 1.5
+      till_alpha = 5.0
+      till_beta = 5.0
+      rho_limit = 0.0
+    }};
+  }},
+  {{
+    ID = 1;
+    name = "Lucite";
+    sml = {sml:.17e};
+    artificial_viscosity = {{ alpha = 1.0; beta = 2.0; }};
+    eos = {{
+      type = 2
+      shear_modulus = 7.3e7
+      bulk_modulus = 10.1e9
+      yield_stress = 1e7
+      till_rho_0 = 1.18e3
+      till_A = 26.7e9
+      till_B = 26.7e9
+      till_E_0 = 487e6
+      till_E_iv = 4.72e6
+      till_E_cv = 18.2e6
+      till_a = 0.5
+      till_b = 1.5
+      till_alpha = 5.0
+      till_beta = 5.0
+      rho_limit = 0.0
+    }};
+  }}
+);
+"""
+
+
+def nakamura(n_target: int = 905000, seed: int = 1991) -> Scenario:
+    """Nakamura & Fujiwara (1991): 0.2 g lucite bullet hitting a 3 cm basalt sphere at 3.2 km/s, 30 degrees
+    (reference: test_cases/nakamura/input/target.c, projectile.c, create_input.sh).  Cubic lattices, fixed
+    sml = 2.8 lattice spacings, Weibull flaws (k = 5e34, m = 8.5) on the target only, at most 28 per particle."""
+    R = 3e-2
+    delta = ((4.0 / 3.0) * np.pi * R**3 / n_target) ** (1.0 / 3.0)
+    sml = 2.8 * delta
+    rho_t, rho_p = 2.7e3, 1.18e3
+    span = R + 2.0 * delta
+    pts = _lattice([-span] * 3, [span] * 3, delta, 3) + delta * np.array([0.11, 0.23, 0.31])
+    pts = pts[(pts**2).sum(axis=1) <= R * R]
+    pts[:, 0] += np.sin(np.pi / 6.0) * R
+    rp = (0.75 / np.pi * 0.2e-3 / rho_p) ** (1.0 / 3.0)
+    pp = _lattice([-rp - delta] * 3, [rp + delta] * 3, delta, 3)
+    pp = pp[(pp**2).sum(axis=1) <= rp * rp]
+    if pp.shape[0] == 0:
+        pp = np.zeros((1, 3))
+    pp[:, 2] += delta * 3.04 + R + 2.0 * rp
+    n_p, n_t = pp.shape[0], pts.shape[0]
+    n = n_p + n_t
+    x = np.concatenate([pp, pts])
+    v = np.zeros_like(x)
+    v[:n_p, 2] = -3.2e3
+    rho = np.concatenate([np.full(n_p, rho_p), np.full(n_t, rho_t)])
+    mat = np.concatenate([np.ones(n_p, dtype=np.int32), np.zeros(n_t, dtype=np.int32)])
+    rng = np.random.default_rng(seed)
+    sw = read_switches("nakamura")
+    nf_t, fl_t = _weibull_flaws(np.full(n_t, delta**3), 28, rng, weibull_m=8.5, weibull_k=5e34)
+    num_flaws = np.concatenate([np.zeros(n_p, dtype=np.int32), nf_t])
+    flaws = np.zeros((n, sw["MAX_NUM_FLAWS"]))
+    flaws[n_p:, :28] = fl_t
+    return Scenario(
+        "nakamura", 3, x, v, rho * delta**3, _NAKAMURA_CFG.format(sml=sml),
+        rho=rho, e=np.zeros(n), mat=mat, S=np.zeros((n, 9)), d=np.zeros(n), num_flaws=num_flaws, flaws=flaws,
+    )
+
+
 # ---------------------------------------------------------------- giant collisions
 _IRON_TILL = """till_rho_0 = 7.8e3
 till_A = 128.0e9
@@ -540,6 +647,14 @@ def stir(sc: Scenario, seed: int = 1234) -> Scenario:
         sc.alpha[rng.random(n) < 0.05] = 1.0
         sc.alpha[rng.random(n) < 0.01] = 0.995
         sc.h = sc.h * (1.0 + 0.1 * u(n))
+    elif cfgname == "nakamura":
+        sc.v = sc.v + 40.0 * u(n, dim)
+        sc.rho = sc.rho * (1.0 + 0.03 * u(n))
+        sc.e = 2.0e4 * (1.0 + u(n)) + 1.0e3
+        hot = rng.random(n) < 0.03
+        sc.e[hot] = rng.uniform(4.0e6, 3.0e7, size=int(hot.sum()))
+        sc.S = 3.0e9 * u(n, dim * dim)          # straddles the von Mises yield surface (Y = 3.5e9 / 1e7)
+        sc.d = np.clip(0.6 * rng.random(n) - 0.05, 0.0, 1.0)
     else:  # giant_hydro / giant_solid
         sc.v = sc.v + 150.0 * u(n, dim)
         sc.rho = sc.rho * (1.0 + 0.03 * u(n))
@@ -550,6 +665,34 @@ def stir(sc: Scenario, seed: int = 1234) -> Scenario:
         if sw.get("SOLID", 0):
             sc.S = 1.0e8 * u(n, dim * dim)
             sc.d = np.clip(0.45 * rng.random(n) - 0.05, 0.0, 1.0)
+    return sc
+
+
+def with_ignored_material(sc: Scenario) -> Scenario:
+    """Adds a material whose eos.type is EOS_TYPE_IGNORE (-1) and hands it to every 11th particle: the
+    `matEOS[materialId] == EOS_TYPE_IGNORE` half of the reference's deactivation tests (src/boundary.cu:98-145,
+    src/internal_forces.cu:145,271, src/density.cu:66-107).  The `materialId == -1` half is produced by the dump
+    hook (REF_DEACTIVATE), which mimics what BoundaryConditionsAfterIntegratorStep does in a run."""
+    n_mat = len(re.findall(r"\bID\s*=", sc.material_cfg))
+    m = re.search(r"sml\s*=\s*([0-9.eE+-]+)", sc.material_cfg)
+    sml_line = f"    sml = {m.group(1)}\n" if m else ""
+    extra = (f"  {{\n    ID = {n_mat}\n    name = \"ignored\"\n{sml_line}    {_AV}\n"
+             "    eos = {\n      type = -1\n    };\n  }\n);")
+    head = sc.material_cfg.rstrip()
+    assert head.endswith(");")
+    sc.material_cfg = head[:-2].rstrip() + ",\n" + extra + "\n"
+    sc.mat = sc.mat.copy()
+    sc.mat[3::11] = n_mat
+    return sc
+
+
+def with_crush_curve(sc: Scenario, style: int) -> Scenario:
+    """The impact scenario on another crush curve of the p-alpha model (reference: src/pressure.cu:365-440)."""
+    extra = f"crushcurve_style = {style}"
+    if style == 1:
+        extra += "\n      porjutzi_p_transition = 6e8\n      porjutzi_alpha_t = 1.1\n      porjutzi_n1 = 12.0\n      porjutzi_n2 = 3.0"
+        sc.material_cfg = sc.material_cfg.replace("porjutzi_alpha_e = 1.25", "porjutzi_alpha_e = 1.2")
+    sc.material_cfg = sc.material_cfg.replace("crushcurve_style = 0", extra)
     return sc
 
 
@@ -571,4 +714,10 @@ def make(config: str, n: int | None = None, stirred: bool = False) -> Scenario:
         return giant(aneos=True) if n is None else giant(n_target=n, aneos=True)
     if config == "giant_solid":
         return giant(solid=True) if n is None else giant(n_target=n, solid=True)
+    if config == "nakamura":
+        return nakamura() if n is None else nakamura(n_target=n)
+    if config.endswith("_ignore"):
+        return with_ignored_material(stir(make({"giant_ignore": "giant_hydro"}.get(config, config[:-7]), n)))
+    if config.startswith("impact_crush"):
+        return with_crush_curve(stir(make("impact", n)), int(config[-1]))
     raise ValueError(f"unknown config {config!r}")

@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
-CONFIGS = ("shocktube", "sedov", "rings", "impact", "giant_hydro", "giant_solid")
+CONFIGS = ("shocktube", "sedov", "rings", "impact", "giant_hydro", "giant_solid", "nakamura")
 
 
 def lib_path(config: str) -> str:

@@ -36,6 +36,7 @@ declare -A CFGDIR=(
   [impact]="examples/impact"
   [giant_hydro]="examples/giant_collisions/hydro"
   [giant_solid]="examples/giant_collisions/solid"
+  [nakamura]="test_cases/nakamura"
 )
 
 if [ ! -d "$REF/src" ]; then
@@ -44,9 +45,26 @@ if [ ! -d "$REF/src" ]; then
 fi
 
 CONFIGS=("$@")
-if [ ${#CONFIGS[@]} -eq 0 ]; then CONFIGS=(shocktube sedov rings impact giant_hydro giant_solid); fi
+if [ ${#CONFIGS[@]} -eq 0 ]; then CONFIGS=(shocktube sedov rings impact giant_hydro giant_solid nakamura); fi
 
 mkdir -p "$OUT"
+# The reference's SHIPPED inputs (the parity fixtures the reference itself provides) and its shipped
+# parameter.h files are staged next to the binaries: git-ignored like them, they travel to the GPU box with the
+# snapshot and are read there by tests/test_gpu_live_reference.py and tests/test_shipped_parameter_h.py.
+stage_fixture() {  # <name> <reference dir> <files...>
+  local name="$1" dir="$2"; shift 2
+  mkdir -p "$OUT/fixtures/$name"
+  for f in "$@"; do
+    if [ -f "$REF/$dir/$f" ] && [ ! -f "$OUT/fixtures/$name/$f" ]; then install -m 0644 "$REF/$dir/$f" "$OUT/fixtures/$name/$f"; fi
+  done
+}
+stage_fixture impact examples/impact impact.0000.gz material.cfg parameter.h
+stage_fixture giant_hydro examples/giant_collisions/hydro impact.0000.gz material.cfg iron.till.cfg granite.till.cfg parameter.h
+stage_fixture giant_solid examples/giant_collisions/solid impact.0000.gz material.cfg iron.till.cfg granite.till.cfg parameter.h
+stage_fixture shocktube test_cases/shocktube parameter.h material.cfg
+stage_fixture sedov test_cases/sedov parameter.h material.cfg
+stage_fixture rings test_cases/colliding_rings parameter.h material.cfg
+stage_fixture nakamura test_cases/nakamura parameter.h material.cfg
 for spec in "${CONFIGS[@]}"; do
   cfg="${spec%+b200}"
   dropin=0; [ "$spec" != "$cfg" ] && dropin=1

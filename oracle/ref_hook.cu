@@ -17,15 +17,23 @@
  *   3. optionally times REF_TIMED calls after REF_WARMUP warm-up calls with a
  *      cudaEvent pair around each call and prints one summary line
  *      "REF_TIMING n=<N> calls=<K> ms_per_call=<t> updates_per_s=<u>".
+ *   0. REF_EVOLVE=1: before all of that, the reference's OWN rk2Adaptive() (src/rk2adaptive.cu:60-520)
+ *      integrates the input over the command line's -n / -t / -M / -Q, so that dump and timing see
+ *      a state after >= 20 accepted steps (SURVEY 8d second measurement point) instead of the
+ *      pristine step-0 input.  p is then the reference's own (no H1 pin needed).
+ *      REF_EVOLVE=pc does the same with predictor_corrector() (monaghan_pc).
  *
  * Dump container: repeated records { char name[32]; int32 dtype (0=f64,1=i32);
- * int64 count; payload }.
+ * int64 count; payload }.  REF_DUMP_LISTS=2 stores the neighbour lists compacted
+ * ("nbr_idx": the first noi[i] entries of every row, row after row) instead of the
+ * dense N x MAX_NUM_INTERACTIONS array (1-2 GB at 10^6 particles).
  */
 #include "miluph.h"
 #include "timeintegration.h"
 #include "rhs.h"
 #include "parameter.h"
 #include "memory_handling.h"
+#include "pressure.h"
 
 #include <stdint.h>
 #include <stdio.h>
@@ -116,7 +124,30 @@ static void hook_dump(const char *prefix, const char *stage, int with_lists)
     DUMP_F64(dalphadp, N); DUMP_F64(dalphadrho, N); DUMP_F64(f, N);
     DUMP_F64(delpdelrho, N); DUMP_F64(delpdele, N);
 #endif
-    if (with_lists) {
+    if (with_lists == 2) {
+        /* compacted rows, copied in slabs of 65536 particles */
+        const int64_t slab = 65536;
+        int *noi_h = (int *)malloc(sizeof(int) * (size_t)N);
+        int *rows = (int *)malloc(sizeof(int) * (size_t)slab * MAX_NUM_INTERACTIONS);
+        int64_t total = 0, i0, i;
+        char tag[32];
+        int dtype = 1;
+        cudaVerify(cudaMemcpy(noi_h, p_device.noi, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost));
+        for (i = 0; i < N; i++) total += noi_h[i];
+        memset(tag, 0, sizeof(tag));
+        strncpy(tag, "nbr_idx", sizeof(tag) - 1);
+        fwrite(tag, 1, sizeof(tag), f);
+        fwrite(&dtype, sizeof(int), 1, f);
+        fwrite(&total, sizeof(int64_t), 1, f);
+        for (i0 = 0; i0 < N; i0 += slab) {
+            const int64_t cnt = (N - i0 < slab) ? N - i0 : slab;
+            cudaVerify(cudaMemcpy(rows, interactions + i0 * MAX_NUM_INTERACTIONS, sizeof(int) * (size_t)cnt * MAX_NUM_INTERACTIONS,
+                                  cudaMemcpyDeviceToHost));
+            for (i = 0; i < cnt; i++) fwrite(rows + i * MAX_NUM_INTERACTIONS, sizeof(int), (size_t)noi_h[i0 + i], f);
+        }
+        free(rows);
+        free(noi_h);
+    } else if (with_lists) {
         int maxni = MAX_NUM_INTERACTIONS;
         char tag[32];
         int dtype = 1;
@@ -144,9 +175,39 @@ void euler()
     const size_t nbytes = (size_t)numberOfParticles * sizeof(double);
     int k;
 
+    const char *s_evolve = getenv("REF_EVOLVE");
+    const int evolve = (s_evolve && s_evolve[0] && s_evolve[0] != '0') ? 1 : 0;
+
+    if (evolve) {
+        /* the reference's own integrator over -n / -t; afterwards p is bound to p_device again
+         * (src/rk2adaptive.cu:320) and holds the integrated state */
+        if (0 == strcmp(s_evolve, "pc")) {
+            param.integrator_type = MONAGHAN_PC;
+            predictor_corrector();
+        } else {
+            param.integrator_type = RK2_ADAPTIVE;
+            rk2Adaptive();
+        }
+        cudaVerify(cudaDeviceSynchronize());
+        cudaVerify(cudaMemcpyToSymbol(p, &p_device, sizeof(struct Particle)));
+        fprintf(stdout, "REF_EVOLVED t=%.17e\n", currentTime);
+    }
+    {
+        /* REF_DEACTIVATE=<stride>: particles stride/2, stride/2 + stride, ... become deactivated the way a run
+         * deactivates them (materialId = EOS_TYPE_IGNORE, src/boundary.cu:179-180, src/rk2adaptive.cu:1474) */
+        const char *s_deact = getenv("REF_DEACTIVATE");
+        const int stride = s_deact ? atoi(s_deact) : 0;
+        if (stride > 0) {
+            int *mat_h = (int *)malloc(sizeof(int) * (size_t)numberOfParticles);
+            cudaVerify(cudaMemcpy(mat_h, p_device.materialId, sizeof(int) * (size_t)numberOfParticles, cudaMemcpyDeviceToHost));
+            for (k = stride / 2; k < numberOfParticles; k += stride) mat_h[k] = EOS_TYPE_IGNORE;
+            cudaVerify(cudaMemcpy(p_device.materialId, mat_h, sizeof(int) * (size_t)numberOfParticles, cudaMemcpyHostToDevice));
+            free(mat_h);
+        }
+    }
     /* p and p_rhs are bound to p_device by initIntegration() */
-    cudaVerify(cudaMemset(p_device.p, 0, nbytes));
-    if (param.selfgravity) {
+    if (!evolve) cudaVerify(cudaMemset(p_device.p, 0, nbytes));
+    if (param.selfgravity && !evolve) {
         cudaVerify(cudaMemset(p_device.g_ax, 0, nbytes));
 #if DIM > 1
         cudaVerify(cudaMemset(p_device.g_ay, 0, nbytes));
@@ -157,12 +218,60 @@ void euler()
     }
     cudaVerify(cudaDeviceSynchronize());
 
-    if (prefix) {
+    if (prefix && (getenv("REF_SEQ") || getenv("REF_DUMP_STATE_ONLY"))) {
+        hook_dump(prefix, "in", 0);   /* the state only (REF_DUMP_STATE_ONLY: input preparation for bench.py) */
+    } else if (prefix) {
         hook_dump(prefix, "in", 0);
         rightHandSide();
         hook_dump(prefix, "out1", with_lists);
         rightHandSide();
         hook_dump(prefix, "out2", 0);
+    }
+
+    {
+        /* REF_SEQ=<K>: K consecutive rightHandSide() calls (the -g bookkeeping of src/rhs.cu:752-813 spans calls:
+         * every 10th call and whenever > 0.1 % of the particles left their cell the walk runs, otherwise the
+         * stored g_a is re-added); after call REF_SEQ_SHIFT_AT every 50th particle is moved by 3 h in x.
+         * Accelerations after every call go to <prefix>.seq<k>.bin. */
+        const char *s_seq = getenv("REF_SEQ");
+        const char *s_at = getenv("REF_SEQ_SHIFT_AT");
+        const int nseq = s_seq ? atoi(s_seq) : 0, shift_at = s_at ? atoi(s_at) : -1;
+        for (k = 0; prefix && k < nseq; k++) {
+            char fname[1024];
+            FILE *f;
+            const int64_t N = numberOfParticles;
+            rightHandSide();
+            cudaVerify(cudaDeviceSynchronize());
+            snprintf(fname, sizeof(fname), "%s.seq%d.bin", prefix, k);
+            if ((f = fopen(fname, "wb")) == NULL) exit(1);
+            DUMP_F64(ax, N);
+#if DIM > 1
+            DUMP_F64(ay, N);
+#endif
+#if DIM > 2
+            DUMP_F64(az, N);
+#endif
+            if (param.selfgravity) {
+                DUMP_F64(g_ax, N);
+#if DIM > 1
+                DUMP_F64(g_ay, N);
+#endif
+#if DIM > 2
+                DUMP_F64(g_az, N);
+#endif
+            }
+            DUMP_I32(noi, N);
+            fclose(f);
+            if (k == shift_at) {
+                double *xh = (double *)malloc(nbytes), *hh = (double *)malloc(nbytes);
+                int i;
+                cudaVerify(cudaMemcpy(xh, p_device.x, nbytes, cudaMemcpyDeviceToHost));
+                cudaVerify(cudaMemcpy(hh, p_device.h, nbytes, cudaMemcpyDeviceToHost));
+                for (i = 0; i < numberOfParticles; i += 50) xh[i] += 3.0 * hh[i];
+                cudaVerify(cudaMemcpy(p_device.x, xh, nbytes, cudaMemcpyHostToDevice));
+                free(xh); free(hh);
+            }
+        }
     }
 
     if (timed > 0) {

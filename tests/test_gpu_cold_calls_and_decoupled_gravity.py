@@ -1,0 +1,99 @@
+"""GPU: the in-scope paths round 1 left untested.
+
+* the three cold calls the reference makes outside rightHandSide() -- calculatePressure by the writer and the
+  predictor-corrector integrators (src/io.cu:3039, src/predictor_corrector.cu:829), damageLimit at output
+  (src/rk2adaptive.cu:468), initializeSoundspeed at start (src/timeintegration.cu:206) -- against the oracle;
+* `-s -g` (decouplegravity) over 13 consecutive calls against the reference RUN LIVE: the Barnes-Hut walk runs on
+  every 10th call and when more than 0.1 % of the particles left their leaf cell, otherwise the stored g_a is re-added
+  (src/rhs.cu:752-813, src/tree.cu:313-381, src/gravity.cu:36-49)."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+import make_golden
+from miluphcuda_b200 import api, scenarios, state
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _setup(config, n, tmp_path, stirred=True):
+    sc = scenarios.make(config, n, stirred=stirred)
+    cfg = state.write_material_files(sc, str(tmp_path))
+    eng = api.RhsEngine(sc.config, n_max=sc.n, material_cfg=cfg)
+    arrays, meta = state.scenario_arrays(sc, eng.materials)
+    return sc, eng, arrays, meta
+
+
+@pytest.mark.parametrize("config", ["sedov", "impact", "giant_solid", "giant_aneos", "nakamura", "rings"])
+def test_cold_calls_match_oracle(config, tmp_path):
+    sc, eng, arrays, meta = _setup(config, 20000, tmp_path)
+    lib = common.oracle_lib(sc.config)
+    n = meta["n"]
+    rng = np.random.default_rng(5)
+    if "d" in arrays:   # damage outside [0, limit] so that every clamp of damageLimit acts
+        arrays["d"][:] = rng.uniform(-0.2, 1.3, n)
+        arrays["numActiveFlaws"][:] = (arrays["numFlaws"] * rng.uniform(0, 1, n)).astype(np.int32)
+    if "damage_porjutzi" in arrays:
+        arrays["damage_porjutzi"][:] = rng.uniform(-0.2, 1.3, n)
+    arrays["cs"][:] = rng.uniform(100.0, 200.0, n)
+    for call in ("init_soundspeed", "pressure", "damage_limit"):
+        ref = {k: v.copy() for k, v in arrays.items()}
+        view_h = api.make_view(ref, None, n, max_num_flaws=meta["max_num_flaws"], grav_const=eng.materials.grav_const)
+        rc = getattr(lib, "oracle_" + call)(view_h, eng.materials.pointer())
+        assert rc == 0
+        dev = {k: torch.from_numpy(v).cuda() for k, v in arrays.items()}
+        view = api.make_view(dev, None, n, max_num_flaws=meta["max_num_flaws"], grav_const=eng.materials.grav_const)
+        getattr(eng, call)(view)
+        torch.cuda.synchronize()
+        changed = 0
+        for name in ref:
+            got = dev[name].cpu().numpy()
+            if name in api.INT_FIELDS:
+                assert np.array_equal(got, ref[name]), (call, name)
+            else:
+                err = common.field_error(got, ref[name])
+                assert err <= common.RTOL, (call, name, err)
+            changed += int(not np.array_equal(ref[name], arrays[name]))
+        if not (call == "damage_limit" and "d" not in arrays):
+            assert changed > 0, f"{call} changed nothing: the test state does not exercise it"
+        arrays = ref   # the next cold call starts from this one's result
+    eng.close()
+
+
+def test_decoupled_gravity_sequence_against_live_reference(tmp_path):
+    config, n_calls, shift_at = "giant_hydro", 13, 4
+    if not os.path.exists(os.path.join(common.REPO, "oracle", "_ref", f"miluphcuda_{config}")):
+        pytest.skip("reference binary not built")
+    sc = scenarios.make(config, 60000, stirred=True)
+    wd = str(tmp_path)
+    env = {"REF_DUMP": os.path.join(wd, "dump"), "REF_SEQ": str(n_calls), "REF_SEQ_SHIFT_AT": str(shift_at)}
+    make_golden.run_reference(sc, wd, env, decouple=True)
+    d_in = make_golden.read_dump(os.path.join(wd, "dump.in.bin"))
+    cfg = os.path.join(wd, "material.cfg")
+    eng = api.RhsEngine(config, n_max=sc.n, material_cfg=cfg)
+    arrays, meta = state.scenario_arrays(sc, eng.materials)
+    for name, val in d_in.items():
+        if name in arrays and arrays[name].shape == val.shape:
+            arrays[name][:] = val
+    n = meta["n"]
+    dev = {k: torch.from_numpy(v).cuda() for k, v in arrays.items()}
+    view = api.make_view(dev, None, n, max_num_flaws=meta["max_num_flaws"], selfgravity=True, decouplegravity=True,
+                         theta=sc.theta, grav_const=eng.materials.grav_const)
+    walked = []
+    for k in range(n_calls):
+        eng.rhs_eval(view)
+        torch.cuda.synchronize()
+        walked.append(eng.stats()["gravity_recomputed"])
+        ref = make_golden.read_dump(os.path.join(wd, f"dump.seq{k}.bin"))
+        assert np.array_equal(dev["noi"].cpu().numpy(), ref["noi"]), f"call {k}: neighbour counts"
+        for name in ("ax", "ay", "az", "g_ax", "g_ay", "g_az"):
+            err = common.field_error(dev[name].cpu().numpy(), ref[name])
+            assert err <= common.RTOL, (k, name, err)
+        if k == shift_at:
+            dev["x"][::50] += 3.0 * dev["h"][::50]
+    # walk on calls 0 and 10 (every 10th) and on call 5 (2 % of the particles left their cells after call 4)
+    assert walked == [1 if k in (0, shift_at + 1, 10) else 0 for k in range(n_calls)], walked
+    eng.close()
