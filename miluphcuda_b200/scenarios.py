@@ -108,6 +108,12 @@ class Scenario:
                     arrs.append(pa.array(np.ascontiguousarray(self.flaws[:, f]), mask=(nf <= f)))
             table = pa.table(arrs, names=[f"c{k}" for k in range(len(arrs))])
             pacsv.write_csv(table, path, write_options=pacsv.WriteOptions(include_header=False, delimiter=" ", quoting_style="none"))
+            if sw.get("FRAGMENTATION", 0):
+                # the reader wants the newline right after the last value it expects (src/io.cu:1290-1313)
+                with open(path, "rb") as fh:
+                    data = fh.read()
+                with open(path, "wb") as fh:
+                    fh.write(re.sub(rb" +\n", b"\n", data))
             return
         except ImportError:
             pass
@@ -698,7 +704,7 @@ def with_crush_curve(sc: Scenario, style: int) -> Scenario:
 
 def make(config: str, n: int | None = None, stirred: bool = False) -> Scenario:
     """Scenario by config name at roughly n particles (None = the shipped resolution)."""
-    if stirred:
+    if stirred and not (config.endswith("_ignore") or config.startswith("impact_crush")):   # those variants are stirred already
         return stir(make(config, n))
     if config == "shocktube":
         return shocktube() if n is None else shocktube(dx=5e-4 * 3376.0 / n)

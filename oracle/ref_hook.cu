@@ -42,6 +42,7 @@
 
 extern int flag_force_gravity_calc;
 extern int gravity_index;
+extern pthread_t fileIOthread;
 
 static void hook_write(FILE *f, const char *name, int dtype, int64_t count, const void *dev)
 {
@@ -181,6 +182,10 @@ void euler()
     if (evolve) {
         /* the reference's own integrator over -n / -t; afterwards p is bound to p_device again
          * (src/rk2adaptive.cu:320) and holds the integrated state */
+        /* no particle file at the end of the integration (write_particles_to_file falls back to ASCII when neither
+         * format is chosen, src/io.cu:1567-1570; HDF5 is compiled out in this build), only the small .info / log files */
+        param.ascii_output = FALSE;
+        param.hdf5output = TRUE;
         if (0 == strcmp(s_evolve, "pc")) {
             param.integrator_type = MONAGHAN_PC;
             predictor_corrector();
@@ -189,6 +194,7 @@ void euler()
             rk2Adaptive();
         }
         cudaVerify(cudaDeviceSynchronize());
+        if (currentDiskIO) pthread_join(fileIOthread, NULL);   /* the writer thread of the last output step */
         cudaVerify(cudaMemcpyToSymbol(p, &p_device, sizeof(struct Particle)));
         fprintf(stdout, "REF_EVOLVED t=%.17e\n", currentTime);
     }

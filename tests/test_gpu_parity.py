@@ -79,7 +79,7 @@ ORACLE_SIZES = {"shocktube": 20000, "sedov": 40000, "rings": 40000, "impact": 30
 
 @pytest.mark.parametrize("scenario", tuple(common.CONFIGS) + tuple(common.VARIANT_CONFIG))
 def test_cuda_matches_oracle_larger(scenario, tmp_path):
-    sc = scenarios.make(scenario, ORACLE_SIZES[scenario], stirred=True)
+    sc = scenarios.make(scenario, ORACLE_SIZES.get(scenario, 30000), stirred=True)
     config = sc.config
     cfg = state.write_material_files(sc, str(tmp_path))
     mats = api.MaterialTables(config, cfg)
