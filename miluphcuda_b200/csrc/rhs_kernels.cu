@@ -79,25 +79,27 @@ constexpr int kPairUnroll = B200_PAIR_UNROLL;
 #else
 #define PAIR_UNROLL   /* no pragma at all: "#pragma unroll 1" would change the code the compiler emits today */
 #endif
-/* Round-2 experiment knobs of the neighbour search (defaults = the code measured in round 1; DESIGN.md section 3,
- * "Where the stall samples sit"): candidates fetched per loop trip, and fetching the next row's cell_start pair
- * while the current row is scanned. */
-#ifndef B200_SEARCH_UNROLL
-#define B200_SEARCH_UNROLL 4
-#endif
-#ifndef B200_SEARCH_ROW_PREFETCH
-#define B200_SEARCH_ROW_PREFETCH 0
-#endif
-constexpr int kSearchUnroll = B200_SEARCH_UNROLL;
-#ifndef B200_CELL_DIV
-#define B200_CELL_DIV 2.0
+constexpr int kSearchUnroll = 4;   /* candidates fetched per trip of the search loop */
+/* brick of search cells that one run of consecutive threads covers (see k_brick_*): about 60-200 particles */
+#if DIM == 3
+#define BRICK_X (VARIABLE_SML ? 2 : 4)
+#define BRICK_Y (VARIABLE_SML ? 2 : 4)
+#define BRICK_Z (VARIABLE_SML ? 2 : 4)
+#elif DIM == 2
+#define BRICK_X (VARIABLE_SML ? 4 : 8)
+#define BRICK_Y (VARIABLE_SML ? 4 : 8)
+#define BRICK_Z 1
+#else
+#define BRICK_X 32
+#define BRICK_Y 1
+#define BRICK_Z 1
 #endif
 #define PREP_VALUES 11
 #define PREP_THREADS 256
 
 __global__ void __launch_bounds__(PREP_THREADS)
 k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, int max_cells,
-          int use_global, double3 glo, double3 ghi)
+          int use_global, double3 glo, double3 ghi, int seg_launch)
 {
     const b200sph_particle_arrays &p = v.p;
     const b200sph_particle_arrays &pr = v.p_rhs;
@@ -256,6 +258,8 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
         for (int a = 0; a < 3; a++) { d.lo[a] = 0.0; d.hi[a] = 0.0; d.root_centre[a] = 0.0; d.nc[a] = 1; }
         d.root_radius = 0.0; d.cell = 1.0; d.cell_inv = 1.0; d.n_cells = 1; d.h_max = 0.0; d.h_mean = 0.0;
         d.nonfinite = 1;
+        d.brick_ok = 0; d.n_seg = 0;
+        for (int a = 0; a < 3; a++) { d.nb[a] = 1; d.bbits[a] = 0; }
         *dom = d;
         return;
     }
@@ -268,7 +272,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
     double cell = fmin(d.h_max, fmax(r[8], 0.5 * d.h_mean)) * 1.0001;
 #else
     /* fixed h: cells of half the smoothing length, 5x5(x5) stencil clipped to the sphere (k_neighbours) */
-    double cell = d.h_max * (1.0001 / B200_CELL_DIV);
+    double cell = d.h_max * (1.0001 / 2.0);
 #endif
     if (!(cell > 0.0)) cell = 1.0;
     for (;;) {
@@ -287,7 +291,81 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
     }
     d.cell = cell;
     d.cell_inv = 1.0 / cell;
+    /* brick table: one entry per row of BRICK_X cells of every brick, bricks numbered along a Morton curve whose
+     * axes carry as many bits as they need; used when it fits the entries this launch sequence was sized for */
+    {
+        const int B[3] = {BRICK_X, BRICK_Y, BRICK_Z};
+        int bits = 0;
+        for (int a = 0; a < 3; a++) {
+            d.nb[a] = (d.nc[a] + B[a] - 1) / B[a];
+            d.bbits[a] = 0;
+            while ((1 << d.bbits[a]) < d.nb[a]) d.bbits[a]++;
+            bits += d.bbits[a];
+        }
+        const long long n_seg = (1ll << bits) * (BRICK_Y * BRICK_Z);
+        d.brick_ok = (DIM > 1 && bits < 30 && n_seg <= (long long)seg_launch) ? 1 : 0;
+        d.n_seg = d.brick_ok ? (int)n_seg : 0;
+    }
     *dom = d;
+}
+
+/* ------------------------------------------------------------------ brick order of the list-walking kernels
+ * The sorted arrays keep x-adjacent cells contiguous (the search scans rows), but a warp that takes 32 consecutive
+ * sorted slots is a thin line of particles whose neighbours span ~25 rows: every lane gathers from different cache
+ * lines (L1 hit rate 57 % in k_forces, profiles/r01_ncu_full_sedov_v4_summary.csv).  The list-walking kernels
+ * therefore visit the particles brick by brick: thread slot t works on sorted slot order[t], where consecutive t
+ * run through the rows of one BRICK_X x BRICK_Y x BRICK_Z block of cells and the bricks follow a Morton curve.
+ * A warp then owns a compact clump whose neighbour sets overlap heavily.  The order costs no second sort: every
+ * brick row is one contiguous range of the sorted arrays (cell_start), so a count / scan / fill over the row
+ * segments yields it. */
+__device__ __forceinline__ bool brick_segment(const Domain &d, const int *cell_start, int sidx, int &begin, int &count)
+{
+    const int rows = BRICK_Y * BRICK_Z;
+    const int m = sidx / rows, r = sidx - m * rows;
+    int c[3] = {0, 0, 0}, pos = 0;
+    for (int l = 0; l < 10; l++)
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+            if (l < d.bbits[a]) {
+                c[a] |= ((m >> pos) & 1) << l;
+                pos++;
+            }
+    const int cx = c[0] * BRICK_X, cy = c[1] * BRICK_Y + r % BRICK_Y, cz = c[2] * BRICK_Z + r / BRICK_Y;
+    if (cx >= d.nc[0] || cy >= d.nc[1] || cz >= d.nc[2]) {
+        begin = 0;
+        count = 0;
+        return false;
+    }
+    const int row = d.nc[0] * (cy + d.nc[1] * cz);
+    begin = cell_start[row + cx];
+    count = cell_start[row + min(cx + BRICK_X, d.nc[0])] - begin;
+    return true;
+}
+
+__global__ void k_brick_count(const Domain *dom, const int *cell_start, int *seg, int seg_launch)
+{
+    const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx > seg_launch) return;
+    const Domain &d = *dom;
+    int begin, count = 0;
+    if (d.brick_ok && sidx < d.n_seg) brick_segment(d, cell_start, sidx, begin, count);
+    seg[sidx] = count;   /* zero beyond the table: the scan runs over the launch size */
+}
+
+__global__ void k_brick_fill(const Domain *dom, const int *cell_start, const int *seg, int *order, int n, int seg_launch)
+{
+    const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    const Domain &d = *dom;
+    if (!d.brick_ok) {
+        /* 1-D, or a grid whose table would not fit: the sorted order itself */
+        for (int k = sidx; k < n; k += gridDim.x * blockDim.x) order[k] = k;
+        return;
+    }
+    if (sidx >= d.n_seg) return;
+    int begin, count;
+    if (!brick_segment(d, cell_start, sidx, begin, count)) return;
+    int *out = order + seg[sidx];
+    for (int t = 0; t < count; t++) out[t] = begin + t;
 }
 
 __device__ __forceinline__ int cell_coord(double x, double lo, double cell_inv, int nc)
@@ -440,7 +518,7 @@ __device__ __forceinline__ Stencil stencil_of(const Rec4 &pi, const Domain &d)
 }
 
 /* exact FP64 scan; only used for a particle whose pre-filtered candidates do not fit the list */
-__device__ __noinline__ int neighbours_exact(const Sorted &s, const Domain &d, int k, const Rec4 &pi, const Stencil &st)
+__device__ __noinline__ int neighbours_exact(const Sorted &s, const Domain &d, int t, int k, const Rec4 &pi, const Stencil &st)
 {
     const double h2 = __dmul_rn(pi.w, pi.w);
     int cnt = 0;
@@ -453,7 +531,7 @@ __device__ __noinline__ int neighbours_exact(const Sorted &s, const Domain &d, i
                 double dx, dy, dz;
                 const double dd = pair_d2(pi, pj, dx, dy, dz);
                 if (dd < h2 && dd < __dmul_rn(pj.w, pj.w) && j != k && s.mat[j] != EOS_TYPE_IGNORE) {
-                    if (cnt < MAX_NUM_INTERACTIONS) s.nbr[NBR_SLOT(k, cnt)] = j;
+                    if (cnt < MAX_NUM_INTERACTIONS) s.nbr[NBR_SLOT(t, cnt)] = j;
                     cnt++;
                 }
             }
@@ -508,45 +586,20 @@ __device__ __forceinline__ bool search_hit(const float4 &si, float thr_i, const 
     return dd < fminf(thr_i, c.w);
 }
 
-#if B200_SEARCH_ROW_PREFETCH
-/* first and one-past-last sorted slot of the candidates of row (y, z) for particle pi, clipped to the sphere;
- * an empty range when the row cannot hold a neighbour */
-__device__ __forceinline__ void search_row_range(const Sorted &s, const Domain &d, const Stencil &st, const Rec4 &pi, double reach2,
-                                                 double slack, int y, int z, int &jb, int &je)
-{
-    jb = 0; je = 0;
-    double rem = reach2;
-#if DIM > 2
-    const double gz = row_gap(pi.z, d.lo[2], d.cell, z, d.nc[2], slack);
-    rem -= gz * gz;
-#endif
-#if DIM > 1
-    const double gy = row_gap(pi.y, d.lo[1], d.cell, y, d.nc[1], slack);
-    rem -= gy * gy;
-#endif
-    if (rem <= 0.0) return;
-    const double w = (double)__fsqrt_ru(__double2float_ru(rem)) * (1.0 + 1e-6) + slack;
-    const int xa = max(st.x0, cell_coord(pi.x - w, d.lo[0], d.cell_inv, d.nc[0]));
-    const int xb = min(st.x1, cell_coord(pi.x + w, d.lo[0], d.cell_inv, d.nc[0]));
-    const int row = d.nc[0] * (y + d.nc[1] * z);
-    jb = s.cell_start[row + xa];
-    je = s.cell_start[row + xb + 1];
-}
-#endif
-
 __global__ void __launch_bounds__(128)
 k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloDomains *hd, int halo_sums)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_targets) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_targets) return;
     const Domain &d = *dom;
     if (d.nonfinite) {   /* void evaluation (reported by the host): do not scan the degenerate one-cell grid */
-        s.noi[k] = 0;
+        s.noi[t] = 0;
         return;
     }
+    const int k = s.order[t];
     const Rec4 pi = ld_rec(&s.pos4[k]);
     if (hd != nullptr && s.perm[k] >= s.n_owned && (!halo_sums || !halo_copy_needs_list(pi, hd))) {
-        s.noi[k] = 0;
+        s.noi[t] = 0;
         return;
     }
     const float4 si = s.srch[k];
@@ -560,41 +613,9 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloD
      * w = sqrt(h_i^2 - g_y^2 - g_z^2) in x; rows with w^2 <= 0 are skipped.  With cells of half the largest h
      * (k_prepare) this leaves ~120 candidates for ~47 hits instead of the 300 of a 3x3x3 block of h-sized cells. */
     int cnt = 0;
-    int *const base = s.nbr + NBR_SLOT(k, 0);
+    int *const base = s.nbr + NBR_SLOT(t, 0);
     const double reach2 = __dmul_rn(pi.w, pi.w) * (1.0 + 1e-9);
     const double slack = 1e-9 * d.cell;
-#if B200_SEARCH_ROW_PREFETCH
-    {
-        /* rows flattened; the cell_start pair of row r + 1 is requested before the candidates of row r are scanned */
-        const int ny = st.y1 - st.y0 + 1, nrows = ny * (st.z1 - st.z0 + 1);
-        int jb_next, je_next;
-        search_row_range(s, d, st, pi, reach2, slack, st.y0, st.z0, jb_next, je_next);
-        for (int r = 0; r < nrows; r++) {
-            const int jb = jb_next, je = je_next;
-            if (r + 1 < nrows) {
-                const int zr = (r + 1) / ny;
-                search_row_range(s, d, st, pi, reach2, slack, st.y0 + (r + 1) - zr * ny, st.z0 + zr, jb_next, je_next);
-            }
-            if (cnt + (je - jb) <= MAX_NUM_INTERACTIONS) {
-                int *slot = base + cnt * NBR_TILE;
-#pragma unroll kSearchUnroll
-                for (int j = jb; j < je; j++) {
-                    const bool hit = search_hit(si, thr_i, __ldg(&s.srch[j]));
-                    if (hit) *slot = j;
-                    slot += hit ? NBR_TILE : 0;
-                    cnt += hit ? 1 : 0;
-                }
-            } else {
-                for (int j = jb; j < je; j++) {
-                    if (search_hit(si, thr_i, __ldg(&s.srch[j]))) {
-                        if (cnt < MAX_NUM_INTERACTIONS) base[cnt * NBR_TILE] = j;
-                        cnt++;
-                    }
-                }
-            }
-        }
-    }
-#else
     for (int z = st.z0; z <= st.z1; z++) {
 #if DIM > 2
         const double gz = row_gap(pi.z, d.lo[2], d.cell, z, d.nc[2], slack);
@@ -637,16 +658,15 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloD
             }
         }
     }
-#endif
     if (cnt > MAX_NUM_INTERACTIONS) {
         /* more survivors than list slots: decide with the exact test (the reference asserts on the exact count) */
-        cnt = neighbours_exact(s, d, k, pi, st);
+        cnt = neighbours_exact(s, d, t, k, pi, st);
         if (cnt >= MAX_NUM_INTERACTIONS) {
             atomicMin(&flags[0], s.perm[k]);
             cnt = MAX_NUM_INTERACTIONS - 1;
         }
     }
-    s.noi[k] = cnt;   /* list slots in use; the exact count replaces it in the LIST_VALIDATE pass */
+    s.noi[t] = cnt;   /* list slots in use; the exact count replaces it in the LIST_VALIDATE pass */
 }
 
 /* How a pair loop treats the list it walks:
@@ -662,29 +682,29 @@ __device__ __forceinline__ bool pair_is_neighbour(double r2, double h2_i, const 
 }
 
 /* walk a list only to validate it (particles whose pair loop is skipped) */
-__device__ __noinline__ int validate_only(const Sorted &s, int k, const Rec4 &pi, int nslots)
+__device__ __noinline__ int validate_only(const Sorted &s, int t, int k, const Rec4 &pi, int nslots)
 {
     const double h2 = __dmul_rn(pi.w, pi.w);
     int cnt = 0;
     for (int q = 0; q < nslots; q++) {
-        const int j = s.nbr[NBR_SLOT(k, q)];
+        const int j = s.nbr[NBR_SLOT(t, q)];
         const Rec4 pj = ld_rec(&s.pos4[j]);
         double dx, dy, dz;
         const double r2 = pair_d2(pi, pj, dx, dy, dz);
         if (j == k || !pair_is_neighbour(r2, h2, pj)) continue;
-        if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
+        if (cnt != q) s.nbr[NBR_SLOT(t, cnt)] = j;
         cnt++;
     }
     return cnt;
 }
 
-__device__ __forceinline__ int finish_validate(const Sorted &s, int k, int cnt, int *flags)
+__device__ __forceinline__ int finish_validate(const Sorted &s, int t, int k, int cnt, int *flags)
 {
     if (cnt >= MAX_NUM_INTERACTIONS) { /* the reference asserts here (src/tree.cu:917) */
         atomicMin(&flags[0], s.perm[k]);
         cnt = MAX_NUM_INTERACTIONS - 1;
     }
-    s.noi[k] = cnt;
+    s.noi[t] = cnt;
     return cnt;
 }
 
@@ -721,23 +741,6 @@ struct PairRecs {
 #endif
 };
 
-/* B200_PREFETCH_TENSORS_L1 (round-2 experiment knob, default off): the solid force loop prefetches positions,
- * velocities and gas records one pair ahead in registers but has none left (168) for the three tensor records,
- * whose load is then waited for in the iteration that issued it -- 34 % of the stall samples.
- * prefetch.global.L1 needs no register: the next neighbour's tensor lines are requested one iteration early. */
-#ifndef B200_PREFETCH_TENSORS_L1
-#define B200_PREFETCH_TENSORS_L1 0
-#endif
-__device__ __forceinline__ void prefetch_l1(const void *ptr)
-{
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-}
-
-/* B200_PREFETCH_TENSORS: also fetch the solid tensor records one iteration ahead (costs 8*TEN_RECS registers) */
-#ifndef B200_PREFETCH_TENSORS
-#define B200_PREFETCH_TENSORS 0
-#endif
-
 __device__ __forceinline__ void load_tensor_recs(const Sorted &s, int j, PairRecs &r)
 {
 #if SOLID
@@ -751,9 +754,6 @@ __device__ __forceinline__ void load_force_recs(const Sorted &s, int j, PairRecs
     r.p = ld_rec(&s.pos4[j]);
     r.v = ld_rec(&s.vel4[j]);
     r.g = ld_rec(&s.gas4[j]);
-#if B200_PREFETCH_TENSORS
-    load_tensor_recs(s, j, r);
-#endif
 }
 
 /* ------------------------------------------------------------------ k_density */
@@ -761,16 +761,17 @@ template <int MODE>
 __global__ void __launch_bounds__(128)
 k_density(Sorted s, b200sph_view v, double *rho_sorted, int n_targets, int *flags)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_targets) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_targets) return;
+    const int k = s.order[t];
     const int matId = s.mat[k];
     const int i = s.perm[k];
     const Rec4 pi = ld_rec(&s.pos4[k]);
-    const int nslots = s.noi[k];
+    const int nslots = s.noi[t];
 #if INTEGRATE_DENSITY
     if (mat_ignored(matId) || c_mat[matId].density_via_kernel_sum < 1) {
         rho_sorted[k] = v.p.rho[i];
-        if (MODE == LIST_VALIDATE) finish_validate(s, k, validate_only(s, k, pi, nslots), flags);
+        if (MODE == LIST_VALIDATE) finish_validate(s, t, k, validate_only(s, t, k, pi, nslots), flags);
         return;
     }
 #endif
@@ -778,7 +779,7 @@ k_density(Sorted s, b200sph_view v, double *rho_sorted, int n_targets, int *flag
         const double rho = ld_rec(&s.vel4[k]).w * cubic_spline_w(0.0, 1.0 / pi.w);
         rho_sorted[k] = rho;
         v.p.rho[i] = rho;
-        if (MODE == LIST_VALIDATE) finish_validate(s, k, validate_only(s, k, pi, nslots), flags);
+        if (MODE == LIST_VALIDATE) finish_validate(s, t, k, validate_only(s, t, k, pi, nslots), flags);
         return;
     }
     const double hinv_i = 1.0 / pi.w;
@@ -789,8 +790,8 @@ k_density(Sorted s, b200sph_view v, double *rho_sorted, int n_targets, int *flag
     Rec4 pj_next = pi;
     double mj_next = 0.0;
     if (nslots > 0) {
-        j_next = s.nbr[NBR_SLOT(k, 0)];
-        j_next2 = s.nbr[NBR_SLOT(k, min(1, nslots - 1))];
+        j_next = s.nbr[NBR_SLOT(t, 0)];
+        j_next2 = s.nbr[NBR_SLOT(t, min(1, nslots - 1))];
         pj_next = ld_rec(&s.pos4[j_next]);
         mj_next = s.vel4[j_next].w;
     }
@@ -800,14 +801,14 @@ PAIR_UNROLL
         const Rec4 pj = pj_next;
         const double mj = mj_next;
         j_next = j_next2;
-        j_next2 = s.nbr[NBR_SLOT(k, min(q + 2, nslots - 1))];
+        j_next2 = s.nbr[NBR_SLOT(t, min(q + 2, nslots - 1))];
         pj_next = ld_rec(&s.pos4[j_next]);
         mj_next = s.vel4[j_next].w;
         double dx, dy, dz, W, g;
         const double r2 = pair_d2(pi, pj, dx, dy, dz);
         if (MODE != LIST_EXACT && (j == k || !pair_is_neighbour(r2, h2_i, pj))) continue;
         if (MODE == LIST_VALIDATE) {
-            if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
+            if (cnt != q) s.nbr[NBR_SLOT(t, cnt)] = j;
             cnt++;
         }
         if (s.any_eos_ignore && mat_ignored(s.mat[j])) continue;
@@ -829,7 +830,7 @@ PAIR_UNROLL
 #endif
         rho = fma(mj, W, rho);
     }
-    if (MODE == LIST_VALIDATE) finish_validate(s, k, cnt, flags);
+    if (MODE == LIST_VALIDATE) finish_validate(s, t, k, cnt, flags);
     rho_sorted[k] = rho;
     v.p.rho[i] = rho;
 }
@@ -1181,11 +1182,12 @@ template <int MODE>
 __global__ void __launch_bounds__(128)
 k_correction(Sorted s, b200sph_view v, int n_targets, int *flags)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_targets) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_targets) return;
+    const int k = s.order[t];
     const int i = s.perm[k];
     const Rec4 pi = ld_rec(&s.pos4[k]);
-    const int nslots = s.noi[k];
+    const int nslots = s.noi[t];
     double C[DIM][DIM];
 #pragma unroll
     for (int a = 0; a < DIM; a++)
@@ -1204,8 +1206,8 @@ k_correction(Sorted s, b200sph_view v, int n_targets, int *flags)
         Rec4 pj_next = pi;
         double vol_next = 0.0;
         if (nslots > 0) {
-            j_next = s.nbr[NBR_SLOT(k, 0)];
-            j_next2 = s.nbr[NBR_SLOT(k, min(1, nslots - 1))];
+            j_next = s.nbr[NBR_SLOT(t, 0)];
+            j_next2 = s.nbr[NBR_SLOT(t, min(1, nslots - 1))];
             pj_next = ld_rec(&s.pos4[j_next]);
             vol_next = s.gas4[j_next].w;
         }
@@ -1215,14 +1217,14 @@ PAIR_UNROLL
             const Rec4 pj = pj_next;
             const double vol_j = vol_next;   /* m_j / rho_j */
             j_next = j_next2;
-            j_next2 = s.nbr[NBR_SLOT(k, min(q + 2, nslots - 1))];
+            j_next2 = s.nbr[NBR_SLOT(t, min(q + 2, nslots - 1))];
             pj_next = ld_rec(&s.pos4[j_next]);
             vol_next = s.gas4[j_next].w;
             double dr[3], W, g;
             const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
             if (MODE != LIST_EXACT && (j == k || !pair_is_neighbour(r2, h2_i, pj))) continue;
             if (MODE == LIST_VALIDATE) {
-                if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
+                if (cnt != q) s.nbr[NBR_SLOT(t, cnt)] = j;
                 cnt++;
             }
             if (s.any_eos_ignore && mat_ignored(s.mat[j])) continue;
@@ -1245,7 +1247,7 @@ PAIR_UNROLL
                 for (int b = a; b < DIM; b++) A[a][b] = fma(wa, dr[b], A[a][b]);
             }
         }
-        if (MODE == LIST_VALIDATE) finish_validate(s, k, cnt, flags);
+        if (MODE == LIST_VALIDATE) finish_validate(s, t, k, cnt, flags);
 #pragma unroll
         for (int a = 0; a < DIM; a++)
 #pragma unroll
@@ -1269,7 +1271,7 @@ PAIR_UNROLL
                 for (int b = 0; b < DIM; b++) C[a][b] = (a == b) ? 1.0 : 0.0;
         }
     } else if (MODE == LIST_VALIDATE) {
-        finish_validate(s, k, validate_only(s, k, pi, nslots), flags);
+        finish_validate(s, t, k, validate_only(s, t, k, pi, nslots), flags);
     }
     double *ten = reinterpret_cast<double *>(s.ten + (size_t)k * TEN_RECS);
 #pragma unroll
@@ -1312,8 +1314,9 @@ template <int MODE>
 __global__ void FORCES_BOUNDS
 k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_targets) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_targets) return;
+    const int k = s.order[t];
     const int i = s.perm[k];
     const int matId = s.mat[k];
     const b200sph_particle_arrays &p = v.p;
@@ -1322,7 +1325,7 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
     if (i >= s.n_owned) return;   /* halo copy: its owner computes the rates */
     const Rec4 pi = ld_rec(&s.pos4[k]);
     const Rec4 vi = ld_rec(&s.vel4[k]);
-    const int nslots = s.noi[k];
+    const int nslots = s.noi[t];
     int noi = nslots;
 
     const bool active = !(matId == BOUNDARY_PARTICLE_ID || mat_ignored(matId)) && i < v.n_real;
@@ -1388,31 +1391,24 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
         const int art_int_exp = (M.exponent_tensor >= 1.0 && M.exponent_tensor <= 8.0 && M.exponent_tensor == floor(M.exponent_tensor))
                                     ? (int)M.exponent_tensor : 0;
 #endif
-        int j_next = s.nbr[NBR_SLOT(k, 0)];
-        int j_next2 = s.nbr[NBR_SLOT(k, min(1, nslots - 1))];
+        int j_next = s.nbr[NBR_SLOT(t, 0)];
+        int j_next2 = s.nbr[NBR_SLOT(t, min(1, nslots - 1))];
         PairRecs nxt;
         load_force_recs(s, j_next, nxt);
 PAIR_UNROLL
         for (int q = 0; q < nslots; q++) {
             const int j = j_next;
             PairRecs cur = nxt;
-#if !B200_PREFETCH_TENSORS
             load_tensor_recs(s, j, cur);
-#endif
             j_next = j_next2;
-            j_next2 = s.nbr[NBR_SLOT(k, min(q + 2, nslots - 1))];
+            j_next2 = s.nbr[NBR_SLOT(t, min(q + 2, nslots - 1))];
             load_force_recs(s, j_next, nxt);   /* past the end this re-reads the last neighbour (harmless) */
-#if SOLID && B200_PREFETCH_TENSORS_L1
-            /* the NEXT neighbour's tensor records, requested into L1 without a destination register */
-            prefetch_l1(&s.ten[(size_t)j_next * TEN_RECS]);
-            prefetch_l1(&s.ten[(size_t)j_next * TEN_RECS + (TEN_RECS - 1)]);
-#endif
             const Rec4 &pj = cur.p;
             double dr[3], dv[3], W, g;
             const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
             if (MODE != LIST_EXACT && (j == k || !pair_is_neighbour(r2, h2_i, pj))) continue;
             if (MODE == LIST_VALIDATE) {
-                if (cnt != q) s.nbr[NBR_SLOT(k, cnt)] = j;
+                if (cnt != q) s.nbr[NBR_SLOT(t, cnt)] = j;
                 cnt++;
             }
             if (s.any_eos_ignore && mat_ignored(s.mat[j])) continue;
@@ -1488,7 +1484,7 @@ PAIR_UNROLL
                      * 1/(A B) gives 1/A = B/(A B) and 1/B = A/(A B) (rounding-level difference to two divisions) */
                     const double den = fma(smooth * smooth, 1e-2, r2);
                     const double rhobar = 0.5 * (gi.z + gj.z);
-                    const double inv = 1.0 / (den * rhobar);
+                    const double inv = pair_rcp(den * rhobar);
                     const double mu = smooth * vr * (inv * rhobar);
                     muijmax = fmax(muijmax, mu);
                     pij = (av_beta * mu - av_alpha * csbar) * mu * (inv * den);
@@ -1583,9 +1579,9 @@ PAIR_UNROLL
             dhdt = fma(-(1.0 / DIM) * pi.w * gj.w, vvnablaW, dhdt);
 #endif
         }
-        if (MODE == LIST_VALIDATE) noi = finish_validate(s, k, cnt, flags);
+        if (MODE == LIST_VALIDATE) noi = finish_validate(s, t, k, cnt, flags);
     } else if (MODE == LIST_VALIDATE) {
-        noi = finish_validate(s, k, validate_only(s, k, pi, nslots), flags);
+        noi = finish_validate(s, t, k, validate_only(s, t, k, pi, nslots), flags);
     }
     p.noi[i] = noi;
 
@@ -1766,12 +1762,12 @@ PAIR_UNROLL
 /* ------------------------------------------------------------------ export of neighbour lists */
 __global__ void k_export_interactions(Sorted s, int *out, int max_per_row)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= s.n) return;
-    const int i = s.perm[k];
-    const int noi = s.noi[k];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= s.n) return;
+    const int i = s.perm[s.order[t]];
+    const int noi = s.noi[t];
     int *row = out + (size_t)i * max_per_row;
-    for (int q = 0; q < max_per_row; q++) row[q] = (q < noi) ? s.perm[s.nbr[NBR_SLOT(k, q)]] : -1;
+    for (int q = 0; q < max_per_row; q++) row[q] = (q < noi) ? s.perm[s.nbr[NBR_SLOT(t, q)]] : -1;
 }
 
 /* cold calls */
@@ -1899,15 +1895,18 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     int launches = 0;
     const int T = 128;
 
+    /* entries of the brick table this call is launched for: what the previous call needed plus head-room (the table
+     * size is decided on the device by k_prepare; a grid that outgrows the launch falls back to the sorted order) */
+    const int seg_launch = (h->seg_launch > 0) ? min(h->seg_capacity, h->seg_launch + h->seg_launch / 2 + 4096) : h->seg_capacity;
     CU(cudaEventRecord(h->ev[0], st));
     int init_flags[5] = {0x7fffffff, 0, 0, 0, 0};   /* [4]: gravity walk ran out of stack */
     CU(cudaMemcpyAsync(h->d_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
     {
-        const int blocks = min(blocks_for(n, PREP_THREADS), 148 * 4);
+        const int blocks = min(blocks_for(n, PREP_THREADS), h->n_sm * 4);
         double3 glo = make_double3(h->global_lo[0], h->global_lo[1], h->global_lo[2]);
         double3 ghi = make_double3(h->global_hi[0], h->global_hi[1], h->global_hi[2]);
         k_prepare<<<blocks, PREP_THREADS, 0, st>>>(v, h->block_partials, h->block_counter, h->d_domain, h->max_cells,
-                                                   h->have_global_domain, glo, ghi);
+                                                   h->have_global_domain, glo, ghi, seg_launch);
         launches++;
     }
     k_cell_keys<<<blocks_for(n, 256), 256, 0, st>>>(v, h->d_domain, h->keys_in, h->idx_in);
@@ -1916,7 +1915,10 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, h->cub_tmp_bytes, h->keys_in, s.keys, h->idx_in, s.perm, n, 0, h->sort_bits, st));
     k_cell_start<<<blocks_for(n + 1, 256), 256, 0, st>>>(s.keys, n, h->d_domain, s.cell_start);   /* whole warps: no early exit inside */
     k_gather<<<blocks_for(n, 256), 256, 0, st>>>(v, s, h->d_domain);
-    launches += 2;
+    k_brick_count<<<blocks_for(seg_launch + 1, 256), 256, 0, st>>>(h->d_domain, s.cell_start, h->seg, seg_launch);
+    CU(cub::DeviceScan::ExclusiveSum(h->scan_tmp, h->scan_tmp_bytes, h->seg, h->seg, seg_launch + 1, st));
+    k_brick_fill<<<blocks_for(seg_launch, 256), 256, 0, st>>>(h->d_domain, s.cell_start, h->seg, s.order, n, seg_launch);
+    launches += 4;
     CU(cudaEventRecord(h->ev[1], st));
 
     {
@@ -1963,7 +1965,7 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     const int TF = h->forces_threads;
     if (validated) k_forces<LIST_EXACT><<<blocks_for(n_targets, TF), TF, h->pad_smem, st>>>(s, v, n_targets, h->d_flags);
     else k_forces<LIST_VALIDATE><<<blocks_for(n_targets, TF), TF, h->pad_smem, st>>>(s, v, n_targets, h->d_flags);
-    k_list_stats<<<min(blocks_for(n, 256), 148 * 4), 256, 0, st>>>(s, h->d_flags);
+    k_list_stats<<<min(blocks_for(n, 256), h->n_sm * 4), 256, 0, st>>>(s, h->d_flags);
     launches += 2;
     CU(cudaEventRecord(h->ev[6], st));
 
@@ -1983,6 +1985,7 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     b200sph_stats &S = h->stats;
     S.kernel_launches = launches;
     S.n_cells = h->h_domain.n_cells;
+    h->seg_launch = h->h_domain.brick_ok ? h->h_domain.n_seg : 0;
     S.cell_size = h->h_domain.cell;
     S.max_noi = flags[1];
     S.total_noi = (int64_t)(((unsigned long long)(unsigned int)flags[3] << 32) | (unsigned int)flags[2]);
@@ -2062,6 +2065,12 @@ int upload_materials(b200sph_handle *h, const MatParams *host, int n, const Aneo
     CU(cudaMemcpyToSymbol(c_mat, host, sizeof(MatParams) * n));
     CU(cudaMemcpyToSymbol(c_aneos, &tables, sizeof(AneosTables)));
     return 0;
+}
+
+int scan_temp_bytes(int n_items, size_t *bytes)
+{
+    int *k = nullptr;
+    return cub::DeviceScan::ExclusiveSum(nullptr, *bytes, k, k, n_items) == cudaSuccess ? 0 : -1;
 }
 
 int sort_temp_bytes(int n_max, int bits, size_t *bytes)

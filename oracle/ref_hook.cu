@@ -237,7 +237,8 @@ void euler()
     {
         /* REF_SEQ=<K>: K consecutive rightHandSide() calls (the -g bookkeeping of src/rhs.cu:752-813 spans calls:
          * every 10th call and whenever > 0.1 % of the particles left their cell the walk runs, otherwise the
-         * stored g_a is re-added); after call REF_SEQ_SHIFT_AT every 50th particle is moved by 3 h in x.
+         * stored g_a is re-added); between calls every particle drifts by 0.002 h in x, and after call REF_SEQ_SHIFT_AT every
+         * 50th particle jumps by 3 h.
          * Accelerations after every call go to <prefix>.seq<k>.bin. */
         const char *s_seq = getenv("REF_SEQ");
         const char *s_at = getenv("REF_SEQ_SHIFT_AT");
@@ -268,12 +269,16 @@ void euler()
             }
             DUMP_I32(noi, N);
             fclose(f);
-            if (k == shift_at) {
+            {
+                /* every particle drifts by 0.002 h per call (far below a cell: the stored g_a is re-added, and it differs
+                 * measurably from a fresh walk); after call shift_at every 50th particle jumps by 3 h */
                 double *xh = (double *)malloc(nbytes), *hh = (double *)malloc(nbytes);
                 int i;
                 cudaVerify(cudaMemcpy(xh, p_device.x, nbytes, cudaMemcpyDeviceToHost));
                 cudaVerify(cudaMemcpy(hh, p_device.h, nbytes, cudaMemcpyDeviceToHost));
-                for (i = 0; i < numberOfParticles; i += 50) xh[i] += 3.0 * hh[i];
+                for (i = 0; i < numberOfParticles; i++) xh[i] += 0.002 * hh[i];
+                if (k == shift_at)
+                    for (i = 0; i < numberOfParticles; i += 50) xh[i] += 3.0 * hh[i];
                 cudaVerify(cudaMemcpy(p_device.x, xh, nbytes, cudaMemcpyHostToDevice));
                 free(xh); free(hh);
             }

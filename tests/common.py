@@ -147,9 +147,29 @@ def field_error(got: np.ndarray, ref: np.ndarray, min_scale: float = 0.0) -> flo
     return float(err.max()) if err.size else 0.0
 
 
+def deactivated_rows(g):
+    """Particles with materialId == EOS_TYPE_IGNORE (-1) in the golden input, or None.
+
+    For those the reference indexes its material tables with -1 (matEOS[-1], matSml[-1], mat_f_sml_max[-1], ...:
+    src/soundspeed.cu:48, src/tree.cu:940, src/plasticity.cu:150 read out of bounds), so what it leaves in their STATE
+    members (c_s = 0, h = 0, S = 0, and with h = 0 an empty neighbour list) is whatever lies in front of the tables.
+    They are compared on what is defined: rates, frozen velocities, g_a, and their absence from every neighbour set."""
+    if "in_materialId" not in g.files:
+        return None
+    rows = np.asarray(g["in_materialId"]) == -1
+    return rows if rows.any() else None
+
+
+def _drop_rows(a, rows):
+    a = np.asarray(a)
+    per = a.size // rows.size
+    return a.reshape(rows.size, per)[~rows].reshape(-1)
+
+
 def compare_fields(arrays: dict, g, stage: str, fields, rtol: float = RTOL, skip=()) -> dict:
     """{field: error} for every field present both in `arrays` and in the golden stage."""
     report = {}
+    dead = deactivated_rows(g)
     for name in fields:
         if name in skip or name not in arrays:
             continue
@@ -161,7 +181,10 @@ def compare_fields(arrays: dict, g, stage: str, fields, rtol: float = RTOL, skip
             first = golden_expected(g, "out1", name)
             if first is not None and first.shape == ref.shape:
                 min_scale = float(np.sqrt(np.mean(first.astype(np.float64) ** 2)))
-        report[name] = field_error(arrays[name], ref, min_scale)
+        got = arrays[name]
+        if dead is not None and name in STATE_FIELDS and name not in ("vx", "vy", "vz"):
+            got, ref = _drop_rows(got, dead), _drop_rows(ref, dead)
+        report[name] = field_error(got, ref, min_scale)
     return report
 
 
