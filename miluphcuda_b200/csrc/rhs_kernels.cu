@@ -79,7 +79,18 @@ constexpr int kPairUnroll = B200_PAIR_UNROLL;
 #else
 #define PAIR_UNROLL   /* no pragma at all: "#pragma unroll 1" would change the code the compiler emits today */
 #endif
+#ifndef B200_PREFETCH_TENSORS_L1
+#define B200_PREFETCH_TENSORS_L1 0   /* A/B knob of this round's measurement script, see tools/gpu_r2c.sh */
+#endif
 constexpr int kSearchUnroll = 4;   /* candidates fetched per trip of the search loop */
+/* B200_BRICK_ORDER: the list-walking kernels visit the particles brick by brick (k_brick_*) instead of in sorted
+ * (x-row) order.  Measured on a B200 (gpurun_out/r2b, round 2): L1 hit rate of k_forces 57 -> 74 % (sedov), 56 -> 71 %
+ * (impact), but no time gained -- the hydro loops are bound by L1TEX tag throughput and dependent FP64 latency, not by
+ * misses -- while the search loses 20 % (lanes of a warp no longer share rows: 25.3 -> 21.2 active threads per
+ * instruction) and the extra index costs the 3-D solid loop its sixth block per SM (168 -> 172 registers). */
+#ifndef B200_BRICK_ORDER
+#define B200_BRICK_ORDER 0
+#endif
 /* brick of search cells that one run of consecutive threads covers (see k_brick_*): about 60-200 particles */
 #if DIM == 3
 #define BRICK_X (VARIABLE_SML ? 2 : 4)
@@ -318,6 +329,16 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
  * A warp then owns a compact clump whose neighbour sets overlap heavily.  The order costs no second sort: every
  * brick row is one contiguous range of the sorted arrays (cell_start), so a count / scan / fill over the row
  * segments yields it. */
+__device__ __forceinline__ int thread_slot(const Sorted &s, int t)
+{
+#if B200_BRICK_ORDER
+    return s.order[t];
+#else
+    (void)s;
+    return t;
+#endif
+}
+
 __device__ __forceinline__ bool brick_segment(const Domain &d, const int *cell_start, int sidx, int &begin, int &count)
 {
     const int rows = BRICK_Y * BRICK_Z;
@@ -596,7 +617,7 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloD
         s.noi[t] = 0;
         return;
     }
-    const int k = s.order[t];
+    const int k = thread_slot(s, t);
     const Rec4 pi = ld_rec(&s.pos4[k]);
     if (hd != nullptr && s.perm[k] >= s.n_owned && (!halo_sums || !halo_copy_needs_list(pi, hd))) {
         s.noi[t] = 0;
@@ -763,7 +784,7 @@ k_density(Sorted s, b200sph_view v, double *rho_sorted, int n_targets, int *flag
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_targets) return;
-    const int k = s.order[t];
+    const int k = thread_slot(s, t);
     const int matId = s.mat[k];
     const int i = s.perm[k];
     const Rec4 pi = ld_rec(&s.pos4[k]);
@@ -1001,14 +1022,22 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
     /* sound speed first, with the pressure left by the previous call (src/rhs.cu:398 before :458) */
     const double cs = eos_soundspeed(M, rho, e, p.p[i], alpha_in, p.cs[i]);
     p.cs[i] = cs;
-    if (M.eos == EOS_TYPE_IGNORE) {
+    /* A material whose eos.type is IGNORE: calculatePressure and damageLimit skip its particles
+     * (src/pressure.cu:41, src/damage.cu:41) -- p, d and damage_total stay what they were -- while symmetrizeStress,
+     * plasticityModel and set_stress_tensor have no such test and run on them with the stored p and damage_total
+     * (src/timeintegration.cu:116-130, src/plasticity.cu:117-388, src/stress.cu:50-157).  Their pair sums are skipped. */
+    const bool eos_ignored = (M.eos == EOS_TYPE_IGNORE);
+#if !SOLID
+    if (eos_ignored) {
         st_rec(&s.gas4[k], Rec4{0.0, cs, rho, m / rho});
         return;
     }
+#endif
     PorousOut po;
-    double pres = eos_pressure(M, rho, e, cs, alpha_in, po);
+    double pres = eos_ignored ? p.p[i] : eos_pressure(M, rho, e, cs, alpha_in, po);
 #if PALPHA_POROSITY
-    if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN) {
+    if (eos_ignored) {
+    } else if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN) {
         p.dalphadp[i] = po.dalphadp;
         p.dalphadrho[i] = po.dalphadrho;
         p.f[i] = po.f;
@@ -1020,7 +1049,7 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
     }
 #endif
 #if REAL_HYDRO
-    if (pres < 0.0) pres = 0.0;
+    if (pres < 0.0 && !eos_ignored) pres = 0.0;
 #endif
 
 #if SOLID
@@ -1043,7 +1072,11 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
 #if FRAGMENTATION
     /* damageLimit, src/damage.cu:33-82 */
     double damage;
-    {
+    if (eos_ignored) {
+        damage = p.damage_total[i];
+        if (damage > 1.0) damage = 1.0;
+        if (damage < 0.0) damage = 0.0;
+    } else {
         double dmg = p.d[i], dmg_max = 1.0;
         const int nof = p.numFlaws[i], noaf = p.numActiveFlaws[i];
         if (dmg < 0.0) dmg = 0.0;
@@ -1184,7 +1217,7 @@ k_correction(Sorted s, b200sph_view v, int n_targets, int *flags)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_targets) return;
-    const int k = s.order[t];
+    const int k = thread_slot(s, t);
     const int i = s.perm[k];
     const Rec4 pi = ld_rec(&s.pos4[k]);
     const int nslots = s.noi[t];
@@ -1316,7 +1349,7 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_targets) return;
-    const int k = s.order[t];
+    const int k = thread_slot(s, t);
     const int i = s.perm[k];
     const int matId = s.mat[k];
     const b200sph_particle_arrays &p = v.p;
@@ -1403,6 +1436,11 @@ PAIR_UNROLL
             j_next = j_next2;
             j_next2 = s.nbr[NBR_SLOT(t, min(q + 2, nslots - 1))];
             load_force_recs(s, j_next, nxt);   /* past the end this re-reads the last neighbour (harmless) */
+#if SOLID && B200_PREFETCH_TENSORS_L1
+            /* the NEXT neighbour's tensor records, requested into L1 without a destination register */
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(&s.ten[(size_t)j_next * TEN_RECS]));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(&s.ten[(size_t)j_next * TEN_RECS + (TEN_RECS - 1)]));
+#endif
             const Rec4 &pj = cur.p;
             double dr[3], dv[3], W, g;
             const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
@@ -1764,7 +1802,7 @@ __global__ void k_export_interactions(Sorted s, int *out, int max_per_row)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= s.n) return;
-    const int i = s.perm[s.order[t]];
+    const int i = s.perm[thread_slot(s, t)];
     const int noi = s.noi[t];
     int *row = out + (size_t)i * max_per_row;
     for (int q = 0; q < max_per_row; q++) row[q] = (q < noi) ? s.perm[s.nbr[NBR_SLOT(t, q)]] : -1;
@@ -1915,10 +1953,13 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, h->cub_tmp_bytes, h->keys_in, s.keys, h->idx_in, s.perm, n, 0, h->sort_bits, st));
     k_cell_start<<<blocks_for(n + 1, 256), 256, 0, st>>>(s.keys, n, h->d_domain, s.cell_start);   /* whole warps: no early exit inside */
     k_gather<<<blocks_for(n, 256), 256, 0, st>>>(v, s, h->d_domain);
+    launches += 2;
+#if B200_BRICK_ORDER
     k_brick_count<<<blocks_for(seg_launch + 1, 256), 256, 0, st>>>(h->d_domain, s.cell_start, h->seg, seg_launch);
     CU(cub::DeviceScan::ExclusiveSum(h->scan_tmp, h->scan_tmp_bytes, h->seg, h->seg, seg_launch + 1, st));
     k_brick_fill<<<blocks_for(seg_launch, 256), 256, 0, st>>>(h->d_domain, s.cell_start, h->seg, s.order, n, seg_launch);
-    launches += 4;
+    launches += 2;
+#endif
     CU(cudaEventRecord(h->ev[1], st));
 
     {

@@ -94,9 +94,11 @@ def test_decoupled_gravity_sequence_against_live_reference(tmp_path):
         for name in ("ax", "ay", "az", "g_ax", "g_ay", "g_az"):
             err = common.field_error(dev[name].cpu().numpy(), ref[name])
             assert err <= common.RTOL, (k, name, err)
+        dev["x"] += 0.002 * dev["h"]   # slow drift: a re-added g_a differs from a fresh walk far above 1e-9
         if k == shift_at:
             dev["x"][::50] += 3.0 * dev["h"][::50]
-    # walk on calls 0 and 10 (every 10th) and on call 5 (2 % of the particles left their cells after call 4)
-    # (the accelerations above already pin every decision to the reference's; this documents the pattern)
-    assert walked[0] == 1 and walked[shift_at + 1] == 1 and walked[10] == 1 and sum(walked) <= 4, walked
+    # walk on call 0, on call 10 (every 10th), and from call 11 on: 2 % of the particles jumped out of their cells after
+    # call 10 -- the reference never refreshes its position snapshot after the first call (reset_movingparticles is
+    # cleared right after the walk, src/rhs.cu:798), so once that many have left, every later call walks
+    assert walked == [1 if (k == 0 or k >= 10) else 0 for k in range(n_calls)], walked
     eng.close()
