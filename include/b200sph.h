@@ -196,6 +196,55 @@ int b200sph_pressure(b200sph_handle *h, const b200sph_view *view);
 int b200sph_damage_limit(b200sph_handle *h, const b200sph_view *view);
 int b200sph_init_soundspeed(b200sph_handle *h, const b200sph_view *view);
 
+/* Persistent cell order (the reference keeps the input file's order for the whole run,
+ * src/memory_handling.cu, and pays for it with uncoalesced accesses in every kernel).  Puts every non-NULL member of
+ * view->p, view->p_rhs and of the n_extra further buffers (the integrator's rk_device[3]) into the order of the search
+ * cells, all with the SAME permutation: new[k] = old[perm[k]].  Call it at a step boundary, every few hundred steps;
+ * perm_out (device, n ints, may be NULL) receives the permutation so that a writer can restore the input order
+ * (src/io.cu).  Results of later evaluations are the same particles' results, relabelled. */
+int b200sph_reorder(b200sph_handle *h, const b200sph_view *view, const b200sph_particle_arrays *extra, int n_extra,
+                    int *perm_out);
+
+/* ---- rk2_adaptive on the device: the embedded Runge-Kutta 2/3 step of src/rk2adaptive.cu:197-485
+ * with its update kernels (integrateFirst/Second/ThirdStep :700-1130), reductions (limitTimestepCourant/Forces/Damage
+ * :521-695, checkError :1134-1482) and the device-to-device copies between p_device and rk_device[3]
+ * (src/memory_handling.cu:253-522), fused into six streaming kernels around three b200sph_rhs_eval() calls.
+ * Buffers keep the reference's meaning: view->p = p_device, rk[0] = rk_device[RKSTART], rk[1] = [RKFIRST],
+ * rk[2] = [RKSECOND]; all device pointers, owned by the caller. ---- */
+typedef struct b200sph_rk2_params {
+    double rk_epsrel;               /* -Q, param.rk_epsrel */
+    double dt_max;                  /* -M, param.maxtimestep; 0 = the output interval */
+    double first_dt;                /* -F, param.firsttimestep; 0 = unset */
+    /* the RK2_* compile-time switches of include/rk2adaptive.h:39-71, with the shipped values as defaults */
+    int use_courant_limit, use_forces_limit, use_damage_limit;
+    int use_velocity_error, use_density_error, use_energy_error;
+    int limit_pressure_change, limit_alpha_change;
+    double courant_fact, forces_fact;           /* COURANT_FACT, FORCES_FACT (include/timeintegration.h:41-43) */
+    double location_safety, min_vel_change, tiny_density, tiny_energy, timestep_safety, smallest_dt_allowed;
+    double max_damage_change, max_alpha_change, max_pressure_change;
+} b200sph_rk2_params;
+
+typedef struct b200sph_rk2_state {
+    double t;                       /* currentTime */
+    double dt;                      /* step the next attempt uses (dt_host) */
+    double dt_suggested;            /* what the error control suggested last */
+    double dt_done;                 /* size of the last accepted step */
+    int accepted, rejected, rhs_calls, intervals, approaching_output_time;
+    double err[6];                  /* last max errors: position, velocity, density, energy, alpha change, pressure change */
+} b200sph_rk2_state;
+
+int b200sph_rk2_default_params(b200sph_rk2_params *prm);
+/* copy_particles_immutables_device_to_device (src/memory_handling.cu:373-392): m, h, cs, numFlaws of p_device into the
+ * three rk buffers; call once after the buffers are allocated (src/rk2adaptive.cu:116-124). */
+int b200sph_rk2_init(b200sph_handle *h, const b200sph_view *view, const b200sph_particle_arrays rk[3]);
+/* one ACCEPTED step (rejected attempts are repeated inside); state->dt is the step to try */
+int b200sph_rk2_step(b200sph_handle *h, const b200sph_view *view, const b200sph_particle_arrays rk[3],
+                     const b200sph_rk2_params *prm, double t_end, b200sph_rk2_state *state, int *offender);
+/* one output interval [state->t, t_end]: first-step / continuing-step rules of src/rk2adaptive.cu:153-171, steps until
+ * t_end, damageLimit before the output (src/rk2adaptive.cu:464-469).  Zero-initialise `state` before the first call. */
+int b200sph_rk2_advance(b200sph_handle *h, const b200sph_view *view, const b200sph_particle_arrays rk[3],
+                        const b200sph_rk2_params *prm, double t_end, b200sph_rk2_state *state, int *offender);
+
 /* Neighbour lists of the last rhs_eval in the caller's indexing, for parity checks and for the
  * reference writer's /number_of_interactions: row i holds noi[i] neighbour ids (unordered).
  * `interactions` is a device buffer of n*max_per_row ints (the reference's dense layout,

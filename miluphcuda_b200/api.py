@@ -93,6 +93,28 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Rk2Params(C.Structure):
+    """b200sph_rk2_params (include/b200sph.h): -Q / -M / -F and the RK2_* switches of the reference's rk2adaptive.h."""
+    _fields_ = [
+        ("rk_epsrel", C.c_double), ("dt_max", C.c_double), ("first_dt", C.c_double),
+        ("use_courant_limit", C.c_int), ("use_forces_limit", C.c_int), ("use_damage_limit", C.c_int),
+        ("use_velocity_error", C.c_int), ("use_density_error", C.c_int), ("use_energy_error", C.c_int),
+        ("limit_pressure_change", C.c_int), ("limit_alpha_change", C.c_int),
+        ("courant_fact", C.c_double), ("forces_fact", C.c_double),
+        ("location_safety", C.c_double), ("min_vel_change", C.c_double), ("tiny_density", C.c_double), ("tiny_energy", C.c_double),
+        ("timestep_safety", C.c_double), ("smallest_dt_allowed", C.c_double),
+        ("max_damage_change", C.c_double), ("max_alpha_change", C.c_double), ("max_pressure_change", C.c_double),
+    ]
+
+
+class Rk2State(C.Structure):
+    _fields_ = [
+        ("t", C.c_double), ("dt", C.c_double), ("dt_suggested", C.c_double), ("dt_done", C.c_double),
+        ("accepted", C.c_int), ("rejected", C.c_int), ("rhs_calls", C.c_int), ("intervals", C.c_int),
+        ("approaching_output_time", C.c_int), ("err", C.c_double * 6),
+    ]
+
+
 ERRORS = {1: "TOO_MANY_INTERACTIONS", 2: "BAD_ARGUMENT", 3: "SWITCH_MISMATCH", 4: "UNSUPPORTED", 5: "NONFINITE", -1: "CUDA"}
 
 
@@ -122,6 +144,13 @@ _EXPORTS = {
     "b200sph_damage_limit": (C.c_int, [C.c_void_p, C.POINTER(View)]),
     "b200sph_init_soundspeed": (C.c_int, [C.c_void_p, C.POINTER(View)]),
     "b200sph_export_interactions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "b200sph_reorder": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(ParticleArrays), C.c_int, C.c_void_p]),
+    "b200sph_rk2_default_params": (C.c_int, [C.POINTER(Rk2Params)]),
+    "b200sph_rk2_init": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(ParticleArrays)]),
+    "b200sph_rk2_step": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(ParticleArrays), C.POINTER(Rk2Params), C.c_double,
+                                   C.POINTER(Rk2State), C.POINTER(C.c_int)]),
+    "b200sph_rk2_advance": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(ParticleArrays), C.POINTER(Rk2Params), C.c_double,
+                                      C.POINTER(Rk2State), C.POINTER(C.c_int)]),
     "b200sph_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "b200sph_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200sph_set_owned": (C.c_int, [C.c_void_p, C.c_int]),
@@ -324,6 +353,36 @@ class RhsEngine:
 
     def init_soundspeed(self, view: View) -> None:
         self._check(self.lib.b200sph_init_soundspeed(self.handle, C.byref(view)))
+
+    def reorder(self, view: View, extra=None, n_extra: int = 0, perm_out=None) -> None:
+        """Put the caller's buffers (and `extra`, a C array from rk2_buffers) into search-cell order: new[k] = old[perm[k]]."""
+        self._check(self.lib.b200sph_reorder(self.handle, C.byref(view), extra, n_extra, _ptr_of(perm_out) or None))
+
+    # ---- rk2_adaptive on the device (csrc/integrate.cu) ----
+    def rk2_default_params(self) -> Rk2Params:
+        prm = Rk2Params()
+        self._check(self.lib.b200sph_rk2_default_params(C.byref(prm)))
+        return prm
+
+    @staticmethod
+    def rk2_buffers(buffers) -> "C.Array":
+        """C array of three b200sph_particle_arrays (RKSTART, RKFIRST, RKSECOND) from three {field: tensor} dicts."""
+        arr = (ParticleArrays * 3)()
+        for k, fields in enumerate(buffers):
+            for name in PARTICLE_FIELDS:
+                setattr(arr[k], name, _ptr_of(fields.get(name)) or None)
+        return arr
+
+    def rk2_init(self, view: View, rk) -> None:
+        self._check(self.lib.b200sph_rk2_init(self.handle, C.byref(view), rk))
+
+    def rk2_step(self, view: View, rk, prm: Rk2Params, t_end: float, state: Rk2State) -> None:
+        off = C.c_int(-1)
+        self._check(self.lib.b200sph_rk2_step(self.handle, C.byref(view), rk, C.byref(prm), t_end, C.byref(state), C.byref(off)), off.value)
+
+    def rk2_advance(self, view: View, rk, prm: Rk2Params, t_end: float, state: Rk2State) -> None:
+        off = C.c_int(-1)
+        self._check(self.lib.b200sph_rk2_advance(self.handle, C.byref(view), rk, C.byref(prm), t_end, C.byref(state), C.byref(off)), off.value)
 
     def export_interactions(self, device_int_buffer, max_per_row: int) -> None:
         self._check(self.lib.b200sph_export_interactions(self.handle, _ptr_of(device_int_buffer), max_per_row))

@@ -10,7 +10,6 @@
 
 int upload_materials(b200sph_handle *h, const MatParams *host, int n, const AneosTables &tables);
 int sort_temp_bytes(int n_max, int bits, size_t *bytes);
-int scan_temp_bytes(int n_items, size_t *bytes);
 int gravity_tree_create(b200sph_handle *h);
 void gravity_tree_destroy(b200sph_handle *h);
 void halo_state_destroy(b200sph_handle *h);
@@ -107,16 +106,6 @@ extern "C" int b200sph_create(b200sph_handle **out, int n_max, int device, uint6
 #endif
     ALLOC(s.nbr, tiles * NBR_TILE * (size_t)MAX_NUM_INTERACTIONS);
     ALLOC(s.noi, n);
-    ALLOC(s.order, n);
-    h->seg_capacity = (int)(8 * n + 65536 < (size_t)0x3fffffff ? 8 * n + 65536 : (size_t)0x3fffffff);
-    ALLOC(h->seg, (size_t)h->seg_capacity + 1);
-    if (scan_temp_bytes(h->seg_capacity + 1, &h->scan_tmp_bytes) != 0) h->scan_tmp_bytes = 0;
-    {
-        char *tmp = nullptr;
-        ALLOC(tmp, h->scan_tmp_bytes + 16);
-        h->scan_tmp = tmp;
-    }
-    h->seg_launch = 0;
     ALLOC(h->keys_in, n); ALLOC(h->idx_in, n);
     ALLOC(h->rho_sorted, n);
     ALLOC(h->block_partials, (size_t)h->n_sm * 4 * 16 + 16);
@@ -166,8 +155,8 @@ extern "C" int b200sph_destroy(b200sph_handle *h)
     gravity_tree_destroy(h);
     Sorted &s = h->s;
     cudaFree(s.perm); cudaFree(s.keys); cudaFree(s.cell_start); cudaFree(s.pos4); cudaFree(s.vel4); cudaFree(s.gas4);
-    cudaFree(s.mat); cudaFree(s.srch); cudaFree(s.ten); cudaFree(s.nbr); cudaFree(s.noi); cudaFree(s.order);
-    cudaFree(h->seg); cudaFree(h->scan_tmp);
+    cudaFree(s.mat); cudaFree(s.srch); cudaFree(s.ten); cudaFree(s.nbr); cudaFree(s.noi);
+    cudaFree(h->rk_scalars); cudaFree(h->rk_partials); cudaFree(h->rk_counter);
     cudaFree(h->keys_in); cudaFree(h->idx_in); cudaFree(h->rho_sorted); cudaFree(h->block_partials);
     cudaFree(h->block_counter); cudaFree(h->d_flags); cudaFree(h->d_domain); cudaFree(h->cub_tmp);
     cudaFree(h->stage);

@@ -8,4 +8,5 @@
 #include "rhs_kernels.cu"
 #include "gravity.cu"
 #include "halo.cu"
+#include "integrate.cu"
 #include "capi.cu"

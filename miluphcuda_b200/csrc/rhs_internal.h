@@ -15,11 +15,8 @@
  *   gas4[n]   = {p/rho^2 (hydro) or 1/rho^2 (solid), c_s, rho, m/rho}
  *   srch[n]   = {u_x, u_y, u_z, thr} FP32, 16 bytes: conservative pre-filter of the neighbour search
  *   ten[n*TEN_RECS]             sigma/rho^2, correction matrix, R/rho^2 packed (solid)
- *   order[n]                    thread slot -> sorted slot: the list-walking kernels visit the particles brick by brick
- *                               (4x4x4 search cells, bricks along a Morton curve) so that a warp's 32 particles are
- *                               compact in space and their neighbour gathers share cache lines
  *   nbr[(tile*MAX_NUM_INTERACTIONS + k)*32 + lane], noi[n]
- *                               neighbour lists indexed by THREAD slot, interleaved per 32-thread tile so the
+ *                               neighbour lists, interleaved per 32-particle tile so the
  *                               k-th entries of a warp's particles share one 128-byte line
  */
 #ifndef B200SPH_RHS_INTERNAL_H
@@ -94,12 +91,6 @@ struct Domain {
     double h_max, h_mean;
     int nc[3];                  /* cells per axis */
     int n_cells;
-    /* thread order of the list-walking kernels (k_brick_*): bricks of BRICK_X x BRICK_Y x BRICK_Z search cells along a
-     * Morton curve, so that the particles of a warp / block are compact in space and gather from the same lines */
-    int nb[3];                  /* bricks per axis */
-    int bbits[3];               /* bits per axis of the brick index */
-    int n_seg;                  /* row segments (one row of BRICK_X cells of one brick) in the segment table */
-    int brick_ok;               /* 0: table does not fit / 1-D: threads walk the sorted order itself */
     int nonfinite;              /* bounding box or h statistics are NaN/Inf: the evaluation is void */
     int n_frozen;               /* particles whose velocity k_prepare zeroed (deactivated / boundary material) */
 };
@@ -109,7 +100,6 @@ struct Sorted {
     int n_owned;                /* caller indices >= n_owned are halo copies: no rates are produced for them */
     int any_eos_ignore;         /* a material with eos.type IGNORE exists: pair loops must look at mat[j] */
     int *perm;                  /* sorted slot -> caller index */
-    int *order;                 /* thread slot t of the list-walking kernels -> sorted slot (brick order); lists and noi are indexed by t */
     int *keys;
     int *cell_start;
     Rec4 *pos4, *vel4, *gas4;
@@ -154,10 +144,6 @@ struct b200sph_handle {
     double *block_partials;     /* bbox / h reductions */
     unsigned int *block_counter;
     int *d_flags;               /* [0] offender slot (min caller index with overflow), [1] max noi, [2..3] total noi (64 bit) */
-    int *seg;                   /* particles per row segment -> exclusive prefix sums (brick order) */
-    int seg_capacity, seg_launch;
-    void *scan_tmp;
-    size_t scan_tmp_bytes;
     int materials_set;
     int kernel_sum_density;     /* 1 if k_density must run (no INTEGRATE_DENSITY, or a material with density_via_kernel_sum) */
     double *rho_sorted;
@@ -183,6 +169,9 @@ struct b200sph_handle {
     cudaEvent_t hook_wait_before_pointwise;
     void (*hook_after_pointwise)(struct b200sph_handle *, void *);
     void *hook_ctx;
+    void *rk_scalars;           /* integrate.cu: device step state, reduction partials, ticket */
+    double *rk_partials;
+    unsigned int *rk_counter;
     b200sph_stats stats;
     /* gravity */
     struct GravityTree *tree;

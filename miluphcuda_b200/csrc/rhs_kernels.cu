@@ -79,38 +79,13 @@ constexpr int kPairUnroll = B200_PAIR_UNROLL;
 #else
 #define PAIR_UNROLL   /* no pragma at all: "#pragma unroll 1" would change the code the compiler emits today */
 #endif
-#ifndef B200_PREFETCH_TENSORS_L1
-#define B200_PREFETCH_TENSORS_L1 0   /* A/B knob of this round's measurement script, see tools/gpu_r2c.sh */
-#endif
 constexpr int kSearchUnroll = 4;   /* candidates fetched per trip of the search loop */
-/* B200_BRICK_ORDER: the list-walking kernels visit the particles brick by brick (k_brick_*) instead of in sorted
- * (x-row) order.  Measured on a B200 (gpurun_out/r2b, round 2): L1 hit rate of k_forces 57 -> 74 % (sedov), 56 -> 71 %
- * (impact), but no time gained -- the hydro loops are bound by L1TEX tag throughput and dependent FP64 latency, not by
- * misses -- while the search loses 20 % (lanes of a warp no longer share rows: 25.3 -> 21.2 active threads per
- * instruction) and the extra index costs the 3-D solid loop its sixth block per SM (168 -> 172 registers). */
-#ifndef B200_BRICK_ORDER
-#define B200_BRICK_ORDER 0
-#endif
-/* brick of search cells that one run of consecutive threads covers (see k_brick_*): about 60-200 particles */
-#if DIM == 3
-#define BRICK_X (VARIABLE_SML ? 2 : 4)
-#define BRICK_Y (VARIABLE_SML ? 2 : 4)
-#define BRICK_Z (VARIABLE_SML ? 2 : 4)
-#elif DIM == 2
-#define BRICK_X (VARIABLE_SML ? 4 : 8)
-#define BRICK_Y (VARIABLE_SML ? 4 : 8)
-#define BRICK_Z 1
-#else
-#define BRICK_X 32
-#define BRICK_Y 1
-#define BRICK_Z 1
-#endif
 #define PREP_VALUES 11
 #define PREP_THREADS 256
 
 __global__ void __launch_bounds__(PREP_THREADS)
 k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, int max_cells,
-          int use_global, double3 glo, double3 ghi, int seg_launch)
+          int use_global, double3 glo, double3 ghi, int apply_hooks)
 {
     const b200sph_particle_arrays &p = v.p;
     const b200sph_particle_arrays &pr = v.p_rhs;
@@ -118,7 +93,9 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
         const int matId = pr.materialId[i];
-        if (matId == EOS_TYPE_IGNORE || matId == BOUNDARY_PARTICLE_ID) {
+        if (!apply_hooks) {
+            /* b200sph_reorder: only the bounding box and the h statistics are wanted, the state is left alone */
+        } else if (matId == EOS_TYPE_IGNORE || matId == BOUNDARY_PARTICLE_ID) {
             /* BoundaryConditionsBeforeRHS, src/boundary.cu:98-145: deactivated particles are frozen */
             p.vx[i] = 0.0;
 #if DIM > 1
@@ -129,7 +106,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
 #endif
             frozen += 1.0;
         }
-        if (matId >= 0 && matId != BOUNDARY_PARTICLE_ID) {
+        if (apply_hooks && matId >= 0 && matId != BOUNDARY_PARTICLE_ID) {
             const MatParams &M = c_mat[matId];
             if (p.rho[i] < M.density_floor) p.rho[i] = M.density_floor;
             if (p.e && p.e[i] < M.energy_floor) p.e[i] = M.energy_floor;
@@ -269,8 +246,6 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
         for (int a = 0; a < 3; a++) { d.lo[a] = 0.0; d.hi[a] = 0.0; d.root_centre[a] = 0.0; d.nc[a] = 1; }
         d.root_radius = 0.0; d.cell = 1.0; d.cell_inv = 1.0; d.n_cells = 1; d.h_max = 0.0; d.h_mean = 0.0;
         d.nonfinite = 1;
-        d.brick_ok = 0; d.n_seg = 0;
-        for (int a = 0; a < 3; a++) { d.nb[a] = 1; d.bbits[a] = 0; }
         *dom = d;
         return;
     }
@@ -302,91 +277,7 @@ k_prepare(b200sph_view v, double *partials, unsigned int *counter, Domain *dom, 
     }
     d.cell = cell;
     d.cell_inv = 1.0 / cell;
-    /* brick table: one entry per row of BRICK_X cells of every brick, bricks numbered along a Morton curve whose
-     * axes carry as many bits as they need; used when it fits the entries this launch sequence was sized for */
-    {
-        const int B[3] = {BRICK_X, BRICK_Y, BRICK_Z};
-        int bits = 0;
-        for (int a = 0; a < 3; a++) {
-            d.nb[a] = (d.nc[a] + B[a] - 1) / B[a];
-            d.bbits[a] = 0;
-            while ((1 << d.bbits[a]) < d.nb[a]) d.bbits[a]++;
-            bits += d.bbits[a];
-        }
-        const long long n_seg = (1ll << bits) * (BRICK_Y * BRICK_Z);
-        d.brick_ok = (DIM > 1 && bits < 30 && n_seg <= (long long)seg_launch) ? 1 : 0;
-        d.n_seg = d.brick_ok ? (int)n_seg : 0;
-    }
     *dom = d;
-}
-
-/* ------------------------------------------------------------------ brick order of the list-walking kernels
- * The sorted arrays keep x-adjacent cells contiguous (the search scans rows), but a warp that takes 32 consecutive
- * sorted slots is a thin line of particles whose neighbours span ~25 rows: every lane gathers from different cache
- * lines (L1 hit rate 57 % in k_forces, profiles/r01_ncu_full_sedov_v4_summary.csv).  The list-walking kernels
- * therefore visit the particles brick by brick: thread slot t works on sorted slot order[t], where consecutive t
- * run through the rows of one BRICK_X x BRICK_Y x BRICK_Z block of cells and the bricks follow a Morton curve.
- * A warp then owns a compact clump whose neighbour sets overlap heavily.  The order costs no second sort: every
- * brick row is one contiguous range of the sorted arrays (cell_start), so a count / scan / fill over the row
- * segments yields it. */
-__device__ __forceinline__ int thread_slot(const Sorted &s, int t)
-{
-#if B200_BRICK_ORDER
-    return s.order[t];
-#else
-    (void)s;
-    return t;
-#endif
-}
-
-__device__ __forceinline__ bool brick_segment(const Domain &d, const int *cell_start, int sidx, int &begin, int &count)
-{
-    const int rows = BRICK_Y * BRICK_Z;
-    const int m = sidx / rows, r = sidx - m * rows;
-    int c[3] = {0, 0, 0}, pos = 0;
-    for (int l = 0; l < 10; l++)
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-            if (l < d.bbits[a]) {
-                c[a] |= ((m >> pos) & 1) << l;
-                pos++;
-            }
-    const int cx = c[0] * BRICK_X, cy = c[1] * BRICK_Y + r % BRICK_Y, cz = c[2] * BRICK_Z + r / BRICK_Y;
-    if (cx >= d.nc[0] || cy >= d.nc[1] || cz >= d.nc[2]) {
-        begin = 0;
-        count = 0;
-        return false;
-    }
-    const int row = d.nc[0] * (cy + d.nc[1] * cz);
-    begin = cell_start[row + cx];
-    count = cell_start[row + min(cx + BRICK_X, d.nc[0])] - begin;
-    return true;
-}
-
-__global__ void k_brick_count(const Domain *dom, const int *cell_start, int *seg, int seg_launch)
-{
-    const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sidx > seg_launch) return;
-    const Domain &d = *dom;
-    int begin, count = 0;
-    if (d.brick_ok && sidx < d.n_seg) brick_segment(d, cell_start, sidx, begin, count);
-    seg[sidx] = count;   /* zero beyond the table: the scan runs over the launch size */
-}
-
-__global__ void k_brick_fill(const Domain *dom, const int *cell_start, const int *seg, int *order, int n, int seg_launch)
-{
-    const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
-    const Domain &d = *dom;
-    if (!d.brick_ok) {
-        /* 1-D, or a grid whose table would not fit: the sorted order itself */
-        for (int k = sidx; k < n; k += gridDim.x * blockDim.x) order[k] = k;
-        return;
-    }
-    if (sidx >= d.n_seg) return;
-    int begin, count;
-    if (!brick_segment(d, cell_start, sidx, begin, count)) return;
-    int *out = order + seg[sidx];
-    for (int t = 0; t < count; t++) out[t] = begin + t;
 }
 
 __device__ __forceinline__ int cell_coord(double x, double lo, double cell_inv, int nc)
@@ -617,7 +508,7 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloD
         s.noi[t] = 0;
         return;
     }
-    const int k = thread_slot(s, t);
+    const int k = t;
     const Rec4 pi = ld_rec(&s.pos4[k]);
     if (hd != nullptr && s.perm[k] >= s.n_owned && (!halo_sums || !halo_copy_needs_list(pi, hd))) {
         s.noi[t] = 0;
@@ -784,7 +675,7 @@ k_density(Sorted s, b200sph_view v, double *rho_sorted, int n_targets, int *flag
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_targets) return;
-    const int k = thread_slot(s, t);
+    const int k = t;
     const int matId = s.mat[k];
     const int i = s.perm[k];
     const Rec4 pi = ld_rec(&s.pos4[k]);
@@ -1217,7 +1108,7 @@ k_correction(Sorted s, b200sph_view v, int n_targets, int *flags)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_targets) return;
-    const int k = thread_slot(s, t);
+    const int k = t;
     const int i = s.perm[k];
     const Rec4 pi = ld_rec(&s.pos4[k]);
     const int nslots = s.noi[t];
@@ -1349,7 +1240,7 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_targets) return;
-    const int k = thread_slot(s, t);
+    const int k = t;
     const int i = s.perm[k];
     const int matId = s.mat[k];
     const b200sph_particle_arrays &p = v.p;
@@ -1436,11 +1327,6 @@ PAIR_UNROLL
             j_next = j_next2;
             j_next2 = s.nbr[NBR_SLOT(t, min(q + 2, nslots - 1))];
             load_force_recs(s, j_next, nxt);   /* past the end this re-reads the last neighbour (harmless) */
-#if SOLID && B200_PREFETCH_TENSORS_L1
-            /* the NEXT neighbour's tensor records, requested into L1 without a destination register */
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(&s.ten[(size_t)j_next * TEN_RECS]));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(&s.ten[(size_t)j_next * TEN_RECS + (TEN_RECS - 1)]));
-#endif
             const Rec4 &pj = cur.p;
             double dr[3], dv[3], W, g;
             const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
@@ -1522,7 +1408,7 @@ PAIR_UNROLL
                      * 1/(A B) gives 1/A = B/(A B) and 1/B = A/(A B) (rounding-level difference to two divisions) */
                     const double den = fma(smooth * smooth, 1e-2, r2);
                     const double rhobar = 0.5 * (gi.z + gj.z);
-                    const double inv = pair_rcp(den * rhobar);
+                    const double inv = 1.0 / (den * rhobar);
                     const double mu = smooth * vr * (inv * rhobar);
                     muijmax = fmax(muijmax, mu);
                     pij = (av_beta * mu - av_alpha * csbar) * mu * (inv * den);
@@ -1802,7 +1688,7 @@ __global__ void k_export_interactions(Sorted s, int *out, int max_per_row)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= s.n) return;
-    const int i = s.perm[thread_slot(s, t)];
+    const int i = s.perm[t];
     const int noi = s.noi[t];
     int *row = out + (size_t)i * max_per_row;
     for (int q = 0; q < max_per_row; q++) row[q] = (q < noi) ? s.perm[s.nbr[NBR_SLOT(t, q)]] : -1;
@@ -1933,9 +1819,6 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     int launches = 0;
     const int T = 128;
 
-    /* entries of the brick table this call is launched for: what the previous call needed plus head-room (the table
-     * size is decided on the device by k_prepare; a grid that outgrows the launch falls back to the sorted order) */
-    const int seg_launch = (h->seg_launch > 0) ? min(h->seg_capacity, h->seg_launch + h->seg_launch / 2 + 4096) : h->seg_capacity;
     CU(cudaEventRecord(h->ev[0], st));
     int init_flags[5] = {0x7fffffff, 0, 0, 0, 0};   /* [4]: gravity walk ran out of stack */
     CU(cudaMemcpyAsync(h->d_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
@@ -1944,7 +1827,7 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
         double3 glo = make_double3(h->global_lo[0], h->global_lo[1], h->global_lo[2]);
         double3 ghi = make_double3(h->global_hi[0], h->global_hi[1], h->global_hi[2]);
         k_prepare<<<blocks, PREP_THREADS, 0, st>>>(v, h->block_partials, h->block_counter, h->d_domain, h->max_cells,
-                                                   h->have_global_domain, glo, ghi, seg_launch);
+                                                   h->have_global_domain, glo, ghi, 1);
         launches++;
     }
     k_cell_keys<<<blocks_for(n, 256), 256, 0, st>>>(v, h->d_domain, h->keys_in, h->idx_in);
@@ -1954,12 +1837,6 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     k_cell_start<<<blocks_for(n + 1, 256), 256, 0, st>>>(s.keys, n, h->d_domain, s.cell_start);   /* whole warps: no early exit inside */
     k_gather<<<blocks_for(n, 256), 256, 0, st>>>(v, s, h->d_domain);
     launches += 2;
-#if B200_BRICK_ORDER
-    k_brick_count<<<blocks_for(seg_launch + 1, 256), 256, 0, st>>>(h->d_domain, s.cell_start, h->seg, seg_launch);
-    CU(cub::DeviceScan::ExclusiveSum(h->scan_tmp, h->scan_tmp_bytes, h->seg, h->seg, seg_launch + 1, st));
-    k_brick_fill<<<blocks_for(seg_launch, 256), 256, 0, st>>>(h->d_domain, s.cell_start, h->seg, s.order, n, seg_launch);
-    launches += 2;
-#endif
     CU(cudaEventRecord(h->ev[1], st));
 
     {
@@ -2026,7 +1903,6 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     b200sph_stats &S = h->stats;
     S.kernel_launches = launches;
     S.n_cells = h->h_domain.n_cells;
-    h->seg_launch = h->h_domain.brick_ok ? h->h_domain.n_seg : 0;
     S.cell_size = h->h_domain.cell;
     S.max_noi = flags[1];
     S.total_noi = (int64_t)(((unsigned long long)(unsigned int)flags[3] << 32) | (unsigned int)flags[2]);
@@ -2100,18 +1976,112 @@ extern "C" int b200sph_damage_limit(b200sph_handle *h, const b200sph_view *view)
     return B200SPH_OK;
 }
 
+/* ------------------------------------------------------------------ persistent cell order
+ * The library never needed the caller's buffers in any particular order -- it sorts into scratch -- but every kernel
+ * that touches the caller's arrays does so through `perm`, and when the caller's order is unrelated to the cell order
+ * (the reference keeps the order of the input file for the whole run, src/memory_handling.cu) those are scattered
+ * 8-byte accesses: k_pointwise of the impact moves 737 MB at 2.4 TB/s effective (profiles/r01_ncu_full_impact_v4).
+ * b200sph_reorder() puts p_device, the rk buffers and the immutables themselves into cell order, once in a while at a
+ * step boundary; afterwards perm is close to the identity and the same kernels run coalesced. */
+template <typename T>
+__global__ void k_permute_rows(T *dst, const T *src, const int *perm, int n, int per)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)n * per) return;
+    const int k = (int)(e / per), c = (int)(e - (size_t)k * per);
+    dst[e] = src[(size_t)perm[k] * per + c];
+}
+
+struct ReorderItem {
+    void *ptr;
+    int per;       /* values per particle */
+    int bytes;     /* 8 (double) or 4 (int) */
+};
+
+static void reorder_collect(const b200sph_particle_arrays &a, int max_num_flaws, ReorderItem *items, int *count, int cap)
+{
+    auto add = [&](void *ptr, int per, int bytes) {
+        if (!ptr) return;
+        for (int k = 0; k < *count; k++)
+            if (items[k].ptr == ptr) return;   /* p_rhs aliases p in the reference (both are p_device) */
+        if (*count < cap) items[(*count)++] = ReorderItem{ptr, per, bytes};
+    };
+    double *scalars[] = {a.x, a.y, a.z, a.vx, a.vy, a.vz, a.dxdt, a.dydt, a.dzdt, a.ax, a.ay, a.az, a.g_ax, a.g_ay, a.g_az,
+                         a.g_local_cellsize, a.g_x, a.g_y, a.g_z, a.m, a.h, a.h0, a.dhdt, a.rho, a.drhodt, a.p, a.e, a.dedt,
+                         a.local_strain, a.ep, a.edotp, a.plastic_f, a.d, a.damage_total, a.dddt, a.damage_porjutzi,
+                         a.ddamage_porjutzidt, a.muijmax, a.pold, a.alpha_jutzi, a.alpha_jutzi_old, a.dalphadt, a.dalphadp,
+                         a.dalphadrho, a.f, a.delpdelrho, a.delpdele, a.cs};
+    for (double *ptr : scalars) add(ptr, 1, 8);
+    double *tensors[] = {a.S, a.dSdt, a.sigma, a.R, a.tensorialCorrectionMatrix};
+    for (double *ptr : tensors) add(ptr, DD, 8);
+    add(a.flaws, max_num_flaws, 8);
+    int *ints[] = {a.numFlaws, a.numActiveFlaws, a.noi, a.materialId, a.depth};
+    for (int *ptr : ints) add(ptr, 1, 4);
+}
+
+extern "C" int b200sph_reorder(b200sph_handle *h, const b200sph_view *view, const b200sph_particle_arrays *extra, int n_extra,
+                               int *perm_out)
+{
+    if (!h || !view || n_extra < 0 || (n_extra > 0 && !extra)) return B200SPH_ERR_BAD_ARGUMENT;
+    const b200sph_view &v = *view;
+    if (v.n <= 0 || v.n > h->n_max || !h->materials_set || !v.p.x || !v.p.h || !v.p_rhs.materialId) return B200SPH_ERR_BAD_ARGUMENT;
+    if (h->n_owned > 0 && h->n_owned < v.n) {
+        snprintf(h->err, sizeof(h->err), "b200sph_reorder: not with halo copies appended (reorder the owned particles before the exchange)");
+        return B200SPH_ERR_BAD_ARGUMENT;
+    }
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Sorted &s = h->s;
+    const int n = v.n;
+    ReorderItem items[3 * 64];
+    int count = 0;
+    reorder_collect(v.p, v.max_num_flaws, items, &count, 3 * 64);
+    reorder_collect(v.p_rhs, v.max_num_flaws, items, &count, 3 * 64);
+    for (int k = 0; k < n_extra; k++) reorder_collect(extra[k], v.max_num_flaws, items, &count, 3 * 64);
+    /* the neighbour lists are void after a reorder: their storage is the staging buffer */
+    const size_t stage_bytes = ((size_t)(h->n_max + NBR_TILE - 1) / NBR_TILE) * NBR_TILE * (size_t)MAX_NUM_INTERACTIONS * sizeof(int);
+    for (int k = 0; k < count; k++)
+        if ((size_t)n * items[k].per * items[k].bytes > stage_bytes) {
+            snprintf(h->err, sizeof(h->err), "b200sph_reorder: a member with %d values per particle does not fit the staging buffer", items[k].per);
+            return B200SPH_ERR_BAD_ARGUMENT;
+        }
+    {
+        const int blocks = min(blocks_for(n, PREP_THREADS), h->n_sm * 4);
+        double3 glo = make_double3(h->global_lo[0], h->global_lo[1], h->global_lo[2]);
+        double3 ghi = make_double3(h->global_hi[0], h->global_hi[1], h->global_hi[2]);
+        k_prepare<<<blocks, PREP_THREADS, 0, st>>>(v, h->block_partials, h->block_counter, h->d_domain, h->max_cells,
+                                                   h->have_global_domain, glo, ghi, 0);
+    }
+    k_cell_keys<<<blocks_for(n, 256), 256, 0, st>>>(v, h->d_domain, h->keys_in, h->idx_in);
+    CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, h->cub_tmp_bytes, h->keys_in, s.keys, h->idx_in, s.perm, n, 0, h->sort_bits, st));
+    for (int k = 0; k < count; k++) {
+        const size_t elems = (size_t)n * items[k].per;
+        const int blocks = (int)((elems + 255) / 256);
+        if (items[k].bytes == 8)
+            k_permute_rows<double><<<blocks, 256, 0, st>>>((double *)s.nbr, (const double *)items[k].ptr, s.perm, n, items[k].per);
+        else
+            k_permute_rows<int><<<blocks, 256, 0, st>>>((int *)s.nbr, (const int *)items[k].ptr, s.perm, n, items[k].per);
+        CU(cudaMemcpyAsync(items[k].ptr, s.nbr, elems * items[k].bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    if (perm_out) CU(cudaMemcpyAsync(perm_out, s.perm, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(s.noi, 0, sizeof(int) * (size_t)n, st));
+    CU(cudaMemcpyAsync(&h->h_domain, h->d_domain, sizeof(Domain), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (h->h_domain.nonfinite) {
+        snprintf(h->err, sizeof(h->err), "non-finite particle coordinate or smoothing length (NaN/Inf) among the %d particles", n);
+        return B200SPH_ERR_NONFINITE;
+    }
+    h->s.n = 0;   /* b200sph_export_interactions has nothing to export until the next evaluation */
+    return B200SPH_OK;
+}
+
 /* upload of the material tables into constant memory (used by capi.cu) */
 int upload_materials(b200sph_handle *h, const MatParams *host, int n, const AneosTables &tables)
 {
     CU(cudaMemcpyToSymbol(c_mat, host, sizeof(MatParams) * n));
     CU(cudaMemcpyToSymbol(c_aneos, &tables, sizeof(AneosTables)));
     return 0;
-}
-
-int scan_temp_bytes(int n_items, size_t *bytes)
-{
-    int *k = nullptr;
-    return cub::DeviceScan::ExclusiveSum(nullptr, *bytes, k, k, n_items) == cudaSuccess ? 0 : -1;
 }
 
 int sort_temp_bytes(int n_max, int bits, size_t *bytes)

@@ -69,38 +69,7 @@ __device__ __forceinline__ double kernel_norm(double hinv)
 #ifndef B200_RSQRT_OPAQUE
 #define B200_RSQRT_OPAQUE SOLID
 #endif
-/* Reciprocal square root and reciprocal of the pair loops.  rsqrt(double) / the IEEE division are a MUFU seed,
- * Newton steps AND a range check with a slow path; the pair loops only ever see normal, positive arguments (r^2 of
- * two distinct particles, (r^2 + 0.01 h^2) * rho_bar), so B200_FAST_PAIR_MATH takes the 64-bit MUFU seed
- * (rsqrt.approx.ftz.f64 / rcp.approx.ftz.f64, ~20 bits) through two Newton steps (~1 ulp) without the check. */
-#ifndef B200_FAST_PAIR_MATH
-#define B200_FAST_PAIR_MATH 0
-#endif
-__device__ __forceinline__ double pair_rsqrt(double x)
-{
-#if B200_FAST_PAIR_MATH
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double hx = 0.5 * x;
-    y = y * fma(-hx * y, y, 1.5);
-    y = y * fma(-hx * y, y, 1.5);
-    return y;
-#else
-    return rsqrt(x);
-#endif
-}
-__device__ __forceinline__ double pair_rcp(double x)
-{
-#if B200_FAST_PAIR_MATH
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    y = fma(y, fma(-x, y, 1.0), y);
-    y = fma(y, fma(-x, y, 1.0), y);
-    return y;
-#else
-    return 1.0 / x;
-#endif
-}
+__device__ __forceinline__ double pair_rsqrt(double x) { return rsqrt(x); }
 
 __device__ __forceinline__ void cubic_spline(double r2, double hinv, double &W, double &g)
 {
