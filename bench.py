@@ -188,6 +188,63 @@ def time_oracle_port(workload: str, n: int, budget_s: float = 15.0):
     return value, cores, sample, dt / calls * 1e3
 
 
+def single_domain_check(api, torch, dist, multigpu, workload, cfg, full, meta, sc, M, rank, world, local_rank) -> dict:
+    """Rank 0 evaluates the WHOLE particle set as one domain on its GPU and sends every rank the rows it owns; each rank
+    compares them with what the distributed evaluation left in its buffers."""
+    import numpy as np
+    names_all = ("ax", "ay", "az", "drhodt", "dedt", "dhdt", "dSdt", "dddt", "dalphadt", "rho", "p", "cs", "g_ax", "g_ay", "g_az", "noi")
+    n, cap, dev = M["n"], M["capacity"], M["dev"]
+    names = [f for f in names_all if f in dev]
+    n_all = sc.n
+    want, scales = {}, {}
+    if rank == 0:
+        eng1 = api.RhsEngine(workload, n_max=n_all, device=local_rank, material_cfg=cfg)
+        eng1.set_stream(torch.cuda.current_stream().cuda_stream)
+        dev1 = {k: torch.from_numpy(v).cuda() for k, v in full.items()}
+        view1 = api.make_view(dev1, None, n_all, max_num_flaws=meta["max_num_flaws"], selfgravity=meta["selfgravity"], theta=meta["theta"],
+                              grav_const=eng1.materials.grav_const)
+        eng1.rhs_eval(view1)
+        torch.cuda.synchronize()
+        x = np.stack([full[a][:n_all] for a in ["x", "y", "z"][: sc.dim]], axis=1)
+        _, parts = multigpu.morton_partition(x, world)
+        sc_t = torch.tensor([float(torch.sqrt(torch.mean(dev1[f].double() ** 2)).item()) for f in names], dtype=torch.float64, device="cuda")
+        for r in range(world):
+            idx = torch.from_numpy(parts[r]).cuda()
+            for f in names:
+                per = dev1[f].numel() // n_all
+                rows = dev1[f].view(n_all, per)[idx].double().contiguous()
+                if r == 0:
+                    want[f] = rows
+                else:
+                    dist.send(rows, dst=r)
+        eng1.close()
+        del dev1
+    else:
+        sc_t = torch.empty(len(names), dtype=torch.float64, device="cuda")
+        for f in names:
+            per = dev[f].numel() // cap
+            buf = torch.empty((n, per), dtype=torch.float64, device="cuda")
+            dist.recv(buf, src=0)
+            want[f] = buf
+    dist.broadcast(sc_t, src=0)
+    worst, worst_name = 0.0, None
+    for k, f in enumerate(names):
+        if f == "noi":
+            continue
+        per = dev[f].numel() // cap
+        got = dev[f].view(cap, per)[:n].double()
+        denom = torch.clamp(want[f].abs(), min=float(sc_t[k].item()))
+        denom = torch.where(denom > 0, denom, torch.ones_like(denom))
+        err = float(((got - want[f]).abs() / denom).max().item())
+        if err > worst:
+            worst, worst_name = err, f
+    noi_bad = int((dev["noi"][:n].double() != want["noi"].view(-1)).sum().item())
+    torch.cuda.empty_cache()
+    return {"what": "owned particles of every rank vs a single-domain evaluation of all %d particles (rank 0's GPU)" % n_all,
+            "fields": [f for f in names if f != "noi"], "max_rel_err": worst, "worst_field": worst_name, "noi_mismatches": noi_bad,
+            "tolerance": 1e-9}
+
+
 # ----------------------------------------------------------------------------- our arm
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -200,6 +257,8 @@ def main() -> None:
     ap.add_argument("--particles", type=int, default=None, help="particles per GPU (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--halo-headroom", type=float, default=1.6, help="capacity of a rank's buffers over its owned particles")
+    ap.add_argument("--no-parity-check", action="store_true", help="several GPUs: skip the single-domain comparison after the timed region")
     ap.add_argument("--no-reorder", action="store_true", help="keep the generator's particle order (no b200sph_reorder)")
     args = ap.parse_args()
     if args.particles is None:
@@ -266,7 +325,8 @@ def main() -> None:
 
     def measure(full, steps, with_clocks):
         """Warm-up + exactly `steps` timed evaluations of one particle set; device times by CUDA events, max over ranks."""
-        arrays, n, capacity, _, dec = multigpu.scatter_scenario(full, sc.n, sc.dim, meta["max_num_flaws"], rank, world)
+        arrays, n, capacity, mine, dec = multigpu.scatter_scenario(full, sc.n, sc.dim, meta["max_num_flaws"], rank, world,
+                                                                    headroom=args.halo_headroom)
         if capacity not in engines:
             engines[capacity] = api.RhsEngine(workload, n_max=capacity, device=local_rank, material_cfg=cfg)
             engines[capacity].set_stream(stream.cuda_stream)
@@ -313,7 +373,7 @@ def main() -> None:
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        return dict(arrays=arrays, n=n, capacity=capacity, dec=dec, eng=eng, dev=dev, drhs=drhs, stage_ms=stage_ms, launches=launches,
+        return dict(arrays=arrays, n=n, capacity=capacity, dec=dec, eng=eng, dev=dev, drhs=drhs, stage_ms=stage_ms, launches=launches, mine=mine,
                     t_wall=t_wall, clocks=clocks, exch_ms=exch_ms, total_ms=float(t.item()), total_particles=float(cnt.item()),
                     stats=eng.stats())
 
@@ -327,8 +387,22 @@ def main() -> None:
                  "stage_ms_per_step": {k: v / steps0 for k, v in m0["stage_ms"].items()}}
         del m0
         torch.cuda.empty_cache()
-    M = measure(full_evolved if full_evolved is not None else full_step0, args.steps, with_clocks=True)
-    del full_step0, full_evolved
+    full_timed = full_evolved if full_evolved is not None else full_step0
+    M = measure(full_timed, args.steps, with_clocks=True)
+    if rank != 0:
+        full_timed = full_step0 = full_evolved = None   # only rank 0 keeps the whole set (for the parity check)
+
+    # ---- several GPUs: the distributed answer against a SINGLE-DOMAIN evaluation of the whole particle set on this
+    # rank's own GPU (after the timed region): neighbour counts of the owned particles equal, every rate within 1e-9
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = single_domain_check(api, torch, dist, multigpu, workload, cfg, full_timed if rank == 0 else None, meta, sc, M,
+                                     rank, world, local_rank)
+        worst = torch.tensor([parity["max_rel_err"], float(parity["noi_mismatches"])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        parity["max_rel_err"], parity["noi_mismatches"] = float(worst[0].item()), int(worst[1].item())
+        parity["ok"] = bool(parity["max_rel_err"] <= 1e-9 and parity["noi_mismatches"] == 0)
+    del full_step0, full_evolved, full_timed
     arrays, n, capacity, eng, dev, drhs = M["arrays"], M["n"], M["capacity"], M["eng"], M["dev"], M["drhs"]
     stage_ms, launches, t_wall, clocks, exch_ms = M["stage_ms"], M["launches"], M["t_wall"], M["clocks"], M["exch_ms"]
     total_ms, total_particles, stats = M["total_ms"], M["total_particles"], M["stats"]
@@ -444,16 +518,23 @@ def main() -> None:
                                       "the reference keeps the input file's order"), "particles_per_gpu": n_global // world, "particles": int(total_particles),
                    "mean_interactions": total_noi / n, "l2": "512 MiB buffer written between timed steps (untimed)",
                    "timing": "per-step CUDA events on the launching stream, summed over K steps, max over ranks",
-                   "multi_gpu": ("Morton-curve domain decomposition, %d-level halo exchange per evaluation (NCCL all_to_all of the "
-                                 "packed state; the send plan is reused while no particle moved > %.2f h_min and re-decided otherwise: "
-                                 "%d plan builds, %d stale plans in this run)%s"
-                                 % (drhs.halo.levels, drhs.halo.SKIN, drhs.halo.plan_builds, drhs.halo.stale_plans,
+                   "multi_gpu": ("Morton-curve domain decomposition, %d-level state halo per evaluation (NCCL all_to_all of the packed "
+                                 "state)%s; the send plan is reused while no particle moved > %.2f h_min, its verdict %s: "
+                                 "%d plan builds, %d stale plans in this run%s"
+                                 % (drhs.halo.levels,
+                                    " + neighbour-sum exchange (owners deliver density / correction matrix of the copies between the "
+                                    "stages of the evaluation: %d per evaluation)" % (drhs.sum_exchanges // max(1, args.steps + args.warmup))
+                                    if drhs.external_sums else "",
+                                    drhs.halo.SKIN,
+                                    "stays on the device as the evaluation's abort flag" if drhs.halo.device_verdict else "is awaited by the host",
+                                    drhs.halo.plan_builds, drhs.halo.stale_plans,
                                     ", replicated gravity tree (NCCL all_gather of x,y,z,m)" if meta["selfgravity"] else ""))
                    if world > 1 else "single",
                    "rank0": {"owned": n, "halo": drhs.n_total - n, "halo_bytes_sent": drhs.halo.last.get("bytes_sent", 0),
                              "exchange_ms_per_step": exch_ms / args.steps},
                    "ranks": {"columns": ["owned", "halo", "rhs_ms", "exchange_ms"], "rows": per_rank}},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "step0": step0,
+        "parity": parity,
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "search_grid": {"cells": stats["n_cells"], "cell_size": stats["cell_size"], "max_interactions": stats["max_noi"]},
     }

@@ -22,6 +22,8 @@
  *   2  B200SPH_ERR_BAD_ARGUMENT
  *   3  B200SPH_ERR_SWITCH_MISMATCH
  *   4  B200SPH_ERR_UNSUPPORTED            (switch / EOS outside the hot-path scope)
+ *   6  B200SPH_ERR_ABORTED                (multi-GPU: the device flag of b200sph_set_abort_flag() was raised, e.g. by a
+ *                                          stale halo plan; the evaluation left the caller's state untouched)
  *   5  B200SPH_ERR_NONFINITE              (a particle coordinate or smoothing length is NaN/Inf; the reference
  *                                          runs out of tree nodes in that situation, src/tree.cu:190-193)
  * `b200sph_last_error()` returns a human-readable description.
@@ -44,6 +46,7 @@ extern "C" {
 #define B200SPH_ERR_SWITCH_MISMATCH 3
 #define B200SPH_ERR_UNSUPPORTED 4
 #define B200SPH_ERR_NONFINITE 5
+#define B200SPH_ERR_ABORTED 6    /* the caller's abort flag was set: nothing was modified, evaluate again */
 #define B200SPH_ERR_CUDA (-1)
 
 /* Field-for-field mirror of the in-scope members of the reference's
@@ -313,6 +316,28 @@ int b200sph_halo_pack_by_rank(b200sph_handle *h, const b200sph_halo_field *field
                               const int *counts, int n_ranks, int n_rows, double *out);
 int b200sph_halo_unpack_by_rank(b200sph_handle *h, const b200sph_halo_field *fields, int n_fields, const double *in,
                                 const int *counts, int n_ranks, int n_rows, int first_row);
+/* ---- neighbour-sum exchange.  With external halo sums a halo copy needs no neighbours of its own:
+ * its kernel-sum density and its tensorial correction matrix are computed by its owner and delivered between the
+ * stages of the evaluation, so ONE halo level suffices (half the copies of the two-level halo, and none of them is
+ * searched for).  b200sph_rhs_eval_stage(.., 0, ..) runs hooks, sort, search and the density sum of the owned
+ * particles and reports B200SPH_SUM_DENSITY when the owners' view->p.rho must now be delivered into the halo rows;
+ * stage 1 runs the pointwise chain and the correction matrices (B200SPH_SUM_CORRECTION: tensorialCorrectionMatrix);
+ * stage 2 the pair forces, gravity and the end-of-call checks.  Stages 0 and 1 only enqueue work on the handle's
+ * stream: a stream-ordered exchange (b200sph_halo_pack_by_rank -> NCCL -> b200sph_halo_unpack_by_rank) needs no host
+ * synchronisation in between. ---- */
+#define B200SPH_SUM_DENSITY 1
+#define B200SPH_SUM_CORRECTION 2
+int b200sph_set_halo_sums(b200sph_handle *h, int external);
+int b200sph_rhs_eval_stage(b200sph_handle *h, const b200sph_view *view, int stage, int *pending_sum, int *offender);
+/* Device flag (an int in device memory, may be NULL to clear) that every state-modifying kernel of an evaluation reads
+ * first: when it is non-zero the evaluation does nothing and returns B200SPH_ERR_ABORTED.  The multi-GPU host points
+ * it at the all-reduced verdict of b200sph_halo_plan_check(): a stale send plan is then discovered at the end-of-call
+ * synchronisation that exists anyway, instead of by a host wait before every evaluation. */
+int b200sph_set_abort_flag(b200sph_handle *h, const int *device_flag);
+/* margins of a reusable send plan for the copies that still need their own lists (two-level halo without the
+ * neighbour-sum exchange): reach = h * reach_scale + skin, the same numbers the plan was selected with */
+int b200sph_halo_set_list_margin(b200sph_handle *h, double reach_scale, double skin);
+
 /* Multi-GPU self-gravity with a replicated tree.  x,y,z,m (device pointers, n_sources doubles each; y/z may
  * be NULL below DIM 2/3) describe the WHOLE particle set in a rank-independent order, normally the
  * all-gather of every rank's owned particles; the caller's owned particles are the block

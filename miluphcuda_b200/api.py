@@ -115,7 +115,7 @@ class Rk2State(C.Structure):
     ]
 
 
-ERRORS = {1: "TOO_MANY_INTERACTIONS", 2: "BAD_ARGUMENT", 3: "SWITCH_MISMATCH", 4: "UNSUPPORTED", 5: "NONFINITE", -1: "CUDA"}
+ERRORS = {1: "TOO_MANY_INTERACTIONS", 2: "BAD_ARGUMENT", 3: "SWITCH_MISMATCH", 4: "UNSUPPORTED", 5: "NONFINITE", 6: "ABORTED", -1: "CUDA"}
 
 
 class B200SphError(RuntimeError):
@@ -168,6 +168,10 @@ _EXPORTS = {
     "b200sph_halo_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "b200sph_halo_pack_by_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200sph_halo_unpack_by_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "b200sph_set_halo_sums": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200sph_rhs_eval_stage": (C.c_int, [C.c_void_p, C.POINTER(View), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200sph_set_abort_flag": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200sph_halo_set_list_margin": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "b200sph_set_gravity_sources": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
 }
 _LIBS: dict = {}
@@ -337,6 +341,24 @@ class RhsEngine:
         rc = self.lib.b200sph_rhs_eval_host(self.handle, C.byref(view), C.byref(off), C.byref(h2d), C.byref(d2h))
         self._check(rc, off.value)
         return h2d.value, d2h.value
+
+    SUM_DENSITY, SUM_CORRECTION, ERR_ABORTED = 1, 2, 6
+
+    def set_halo_sums(self, external: bool) -> None:
+        self._check(self.lib.b200sph_set_halo_sums(self.handle, int(bool(external))))
+
+    def rhs_eval_stage(self, view: View, stage: int) -> int:
+        """One stage (0, 1, 2) of the evaluation; returns the neighbour sum (SUM_*) the host must deliver before the next."""
+        pending, off = C.c_int(0), C.c_int(-1)
+        rc = self.lib.b200sph_rhs_eval_stage(self.handle, C.byref(view), stage, C.byref(pending), C.byref(off))
+        self._check(rc, off.value)
+        return pending.value
+
+    def set_abort_flag(self, device_flag) -> None:
+        self._check(self.lib.b200sph_set_abort_flag(self.handle, _ptr_of(device_flag) or None))
+
+    def halo_set_list_margin(self, reach_scale: float, skin: float) -> None:
+        self._check(self.lib.b200sph_halo_set_list_margin(self.handle, float(reach_scale), float(skin)))
 
     HOST_CACHE_IMMUTABLES = 1
     HOST_SKIP_SCRATCH = 2

@@ -59,6 +59,7 @@ extern "C" int b200sph_halo_set_domains(b200sph_handle *h, const double *boxes, 
     HaloDomains &d = st->host;
     memset(&d, 0, sizeof(d));
     d.n_boxes = n_boxes; d.n_ranks = n_ranks; d.my_rank = my_rank; d.my_first = -1;
+    d.list_reach_scale = 1.0; d.list_skin = 0.0;
     int per_rank[HALO_MAX_RANKS] = {0};
     for (int b = 0; b < n_boxes; b++) {
         const int r = box_rank[b];
@@ -74,6 +75,31 @@ extern "C" int b200sph_halo_set_domains(b200sph_handle *h, const double *boxes, 
     d.my_count = per_rank[my_rank];
     if (d.my_first < 0) d.my_first = 0;
     HCU(cudaMemcpy(st->dev, &d, sizeof(HaloDomains), cudaMemcpyHostToDevice));
+    return B200SPH_OK;
+}
+
+extern "C" int b200sph_halo_set_list_margin(b200sph_handle *h, double reach_scale, double skin)
+{
+    if (!h || !h->halo || !(reach_scale >= 1.0) || !(skin >= 0.0)) return B200SPH_ERR_BAD_ARGUMENT;
+    HaloState *st = (HaloState *)h->halo;
+    HCU(cudaSetDevice(h->device));
+    st->host.list_reach_scale = reach_scale;
+    st->host.list_skin = skin;
+    HCU(cudaMemcpyAsync(&st->dev->list_reach_scale, &st->host.list_reach_scale, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return B200SPH_OK;
+}
+
+extern "C" int b200sph_set_halo_sums(b200sph_handle *h, int external)
+{
+    if (!h) return B200SPH_ERR_BAD_ARGUMENT;
+    h->halo_sums_external = external ? 1 : 0;
+    return B200SPH_OK;
+}
+
+extern "C" int b200sph_set_abort_flag(b200sph_handle *h, const int *device_flag)
+{
+    if (!h) return B200SPH_ERR_BAD_ARGUMENT;
+    h->abort_flag = device_flag;
     return B200SPH_OK;
 }
 

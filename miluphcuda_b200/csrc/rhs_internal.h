@@ -99,6 +99,8 @@ struct Sorted {
     int n;
     int n_owned;                /* caller indices >= n_owned are halo copies: no rates are produced for them */
     int any_eos_ignore;         /* a material with eos.type IGNORE exists: pair loops must look at mat[j] */
+    int halo_sums_external;     /* multi-GPU: density / correction matrix of halo copies are delivered by their owners */
+    const int *abort;           /* device flag (may be NULL): non-zero = this evaluation must not touch the caller's state */
     int *perm;                  /* sorted slot -> caller index */
     int *keys;
     int *cell_start;
@@ -114,6 +116,7 @@ struct Sorted {
 #define HALO_MAX_RANKS 64
 struct HaloDomains {
     double lo[HALO_MAX_BOXES][3], hi[HALO_MAX_BOXES][3];
+    double list_reach_scale, list_skin;   /* margins of the reusable send plan (halo_copy_needs_list) */
     int rank[HALO_MAX_BOXES];       /* owner of box b */
     int local[HALO_MAX_BOXES];      /* index of box b among its owner's boxes */
     int n_boxes, n_ranks, my_rank, my_first, my_count;
@@ -149,6 +152,9 @@ struct b200sph_handle {
     double *rho_sorted;
     double *aneos_buf;          /* device copy of the tabulated-EOS payload */
     int n_owned;
+    int halo_sums_external;     /* b200sph_set_halo_sums */
+    const int *abort_flag;      /* b200sph_set_abort_flag */
+    int lists_validated, stage_launches;   /* carried between the stages of one evaluation */
     const double *grav_src[4];  /* x, y, z, m of the global particle set (multi-GPU gravity), device pointers */
     int grav_src_n, grav_own_begin;
     int pad_smem;               /* profiling knob (B200SPH_PAD_SMEM): dynamic shared memory per pair-loop block, throttles occupancy */

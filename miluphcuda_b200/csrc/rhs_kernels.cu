@@ -457,7 +457,9 @@ __device__ __noinline__ int neighbours_exact(const Sorted &s, const Domain &d, i
  * outer halo level (copies that only complete those sums) and every copy of a one-level halo skip the search. */
 __device__ __forceinline__ bool halo_copy_needs_list(const Rec4 &pi, const HaloDomains *hd)
 {
-    const double reach = pi.w * (1.0 + 1e-9);
+    /* the send plan lets owned particles drift up to its skin out of their boxes and h grow by its growth factor
+     * before it is rebuilt: a copy can then be a neighbour of an owned particle from that much further away */
+    const double reach = pi.w * hd->list_reach_scale * (1.0 + 1e-9) + hd->list_skin;
     const double reach2 = reach * reach;
     const double pos[3] = {pi.x, pi.y, pi.z};
     const int first = hd->my_first, count = hd->my_count;
@@ -510,7 +512,7 @@ k_neighbours(Sorted s, const Domain *dom, int n_targets, int *flags, const HaloD
     }
     const int k = t;
     const Rec4 pi = ld_rec(&s.pos4[k]);
-    if (hd != nullptr && s.perm[k] >= s.n_owned && (!halo_sums || !halo_copy_needs_list(pi, hd))) {
+    if (s.perm[k] >= s.n_owned && (s.halo_sums_external || (hd != nullptr && (!halo_sums || !halo_copy_needs_list(pi, hd))))) {
         s.noi[t] = 0;
         return;
     }
@@ -680,6 +682,8 @@ k_density(Sorted s, b200sph_view v, double *rho_sorted, int n_targets, int *flag
     const int i = s.perm[k];
     const Rec4 pi = ld_rec(&s.pos4[k]);
     const int nslots = s.noi[t];
+    if (s.abort && *s.abort) return;
+    if (s.halo_sums_external && i >= s.n_owned) return;   /* the owner sends this copy's density (b200sph_rhs_eval_stage) */
 #if INTEGRATE_DENSITY
     if (mat_ignored(matId) || c_mat[matId].density_via_kernel_sum < 1) {
         rho_sorted[k] = v.p.rho[i];
@@ -896,8 +900,9 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
     const b200sph_particle_arrays &p = v.p;
     const b200sph_particle_arrays &pr = v.p_rhs;
     (void)pr;   /* only the solid switch sets write p_rhs scratch here */
+    if (s.abort && *s.abort) return;
     const double m = s.vel4[k].w;
-    double rho = use_rho_sorted ? rho_sorted[k] : p.rho[i];
+    double rho = (use_rho_sorted && !(s.halo_sums_external && i >= s.n_owned)) ? rho_sorted[k] : p.rho[i];
 
     if (matId < 0) { /* deactivated particle: never a neighbour, keep the records finite */
         st_rec(&s.gas4[k], Rec4{0.0, 0.0, rho, 0.0});
@@ -1112,6 +1117,7 @@ k_correction(Sorted s, b200sph_view v, int n_targets, int *flags)
     const int i = s.perm[k];
     const Rec4 pi = ld_rec(&s.pos4[k]);
     const int nslots = s.noi[t];
+    if (s.halo_sums_external && i >= s.n_owned) return;   /* the owner sends this copy's matrix; k_import_correction stores it */
     double C[DIM][DIM];
 #pragma unroll
     for (int a = 0; a < DIM; a++)
@@ -1208,6 +1214,24 @@ PAIR_UNROLL
 }
 #endif
 
+#if TENSORIAL_CORRECTION
+/* Multi-GPU, neighbour-sum exchange: the correction matrices of the halo copies arrived in the caller's rows
+ * (tensorialCorrectionMatrix, row-major DIM x DIM); the force loop reads them from the packed sorted records. */
+__global__ void k_import_correction(Sorted s, b200sph_view v)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= s.n) return;
+    const int i = s.perm[k];
+    if (i < s.n_owned) return;
+    double *ten = reinterpret_cast<double *>(s.ten + (size_t)k * TEN_RECS);
+    const double *C = v.p_rhs.tensorialCorrectionMatrix + (size_t)i * DD;
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = a; b < DIM; b++) ten[ten_c(a, b)] = C[a * DIM + b];
+}
+#endif
+
 /* ------------------------------------------------------------------ k_forces */
 __device__ __forceinline__ double int_power(double x, int n)
 {
@@ -1247,6 +1271,7 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
     const b200sph_particle_arrays &pr = v.p_rhs;
     (void)pr;
     if (i >= s.n_owned) return;   /* halo copy: its owner computes the rates */
+    if (s.abort && *s.abort) return;
     const Rec4 pi = ld_rec(&s.pos4[k]);
     const Rec4 vi = ld_rec(&s.vel4[k]);
     const int nslots = s.noi[t];
@@ -1792,7 +1817,7 @@ int gravity_tree_create(b200sph_handle *h);
 void gravity_tree_destroy(b200sph_handle *h);
 int gravity_eval(b200sph_handle *h, const b200sph_view &v, int *launches);
 
-extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int *offender)
+static int rhs_check_view(b200sph_handle *h, const b200sph_view *view)
 {
     if (!h || !view) return B200SPH_ERR_BAD_ARGUMENT;
     const b200sph_view &v = *view;
@@ -1809,15 +1834,20 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
         snprintf(h->err, sizeof(h->err), "view is missing a mandatory array (x, vx, m, h, rho, p, cs, ax, dxdt, drhodt, noi, materialId)");
         return B200SPH_ERR_BAD_ARGUMENT;
     }
-    CU(cudaSetDevice(h->device));
+    return B200SPH_OK;
+}
+
+/* stage 0: boundary hooks, cell sort, neighbour search, kernel-sum density */
+static int rhs_stage_search(b200sph_handle *h, const b200sph_view &v)
+{
     cudaStream_t st = h->stream;
     Sorted &s = h->s;
     s.n = v.n;
     s.n_owned = (h->n_owned > 0 && h->n_owned < v.n) ? h->n_owned : v.n;
-    const int n = v.n;
-    const int n_targets = (h->n_owned > 0 && h->n_owned < n) ? n : n; /* halo particles also need lists (rho, C) */
+    s.halo_sums_external = (h->halo_sums_external && s.n_owned < v.n) ? 1 : 0;
+    s.abort = h->abort_flag;
+    const int n = v.n, T = 128;
     int launches = 0;
-    const int T = 128;
 
     CU(cudaEventRecord(h->ev[0], st));
     int init_flags[5] = {0x7fffffff, 0, 0, 0, 0};   /* [4]: gravity walk ran out of stack */
@@ -1838,12 +1868,12 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     k_gather<<<blocks_for(n, 256), 256, 0, st>>>(v, s, h->d_domain);
     launches += 2;
     CU(cudaEventRecord(h->ev[1], st));
-
     {
-        /* halo copies whose neighbour sums nobody reads skip the search (multi-GPU; boxes from b200sph_halo_set_domains) */
+        /* halo copies whose neighbour sums nobody reads skip the search (multi-GPU; boxes from b200sph_halo_set_domains);
+         * with the neighbour-sum exchange no copy is searched for at all */
         const HaloDomains *hd = (h->halo && s.n_owned < n) ? ((HaloState *)h->halo)->dev : nullptr;
         const int halo_sums = (h->kernel_sum_density || TENSORIAL_CORRECTION) ? 1 : 0;
-        k_neighbours<<<blocks_for(n_targets, T), T, 0, st>>>(s, h->d_domain, n_targets, h->d_flags, hd, halo_sums);
+        k_neighbours<<<blocks_for(n, T), T, 0, st>>>(s, h->d_domain, n, h->d_flags, hd, halo_sums);
     }
     launches++;
     CU(cudaEventRecord(h->ev[2], st));
@@ -1852,37 +1882,60 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
      * the exact test and compacts them (LIST_VALIDATE), later loops trust them (LIST_EXACT).
      * kernel-sum density: always without INTEGRATE_DENSITY, else only for materials that ask for it
      * (then it does not visit every particle and only checks, LIST_CHECK). */
-    const int use_rho_sorted = h->kernel_sum_density;
-    double *rho_sorted = h->rho_sorted;
-    int validated = 0;
-    if (use_rho_sorted) {
+    h->lists_validated = 0;
+    if (h->kernel_sum_density) {
 #if INTEGRATE_DENSITY
-        k_density<LIST_CHECK><<<blocks_for(n_targets, T), T, h->pad_smem, st>>>(s, v, rho_sorted, n_targets, h->d_flags);
+        k_density<LIST_CHECK><<<blocks_for(n, T), T, h->pad_smem, st>>>(s, v, h->rho_sorted, n, h->d_flags);
 #else
-        k_density<LIST_VALIDATE><<<blocks_for(n_targets, T), T, h->pad_smem, st>>>(s, v, rho_sorted, n_targets, h->d_flags);
-        validated = 1;
+        k_density<LIST_VALIDATE><<<blocks_for(n, T), T, h->pad_smem, st>>>(s, v, h->rho_sorted, n, h->d_flags);
+        h->lists_validated = 1;
 #endif
         launches++;
     }
     CU(cudaEventRecord(h->ev[3], st));
+    h->stage_launches = launches;
+    return B200SPH_OK;
+}
 
+/* stage 1: the pointwise chain and the tensorial correction */
+static int rhs_stage_pointwise(b200sph_handle *h, const b200sph_view &v)
+{
+    cudaStream_t st = h->stream;
+    Sorted &s = h->s;
+    const int n = v.n, T = 128;
     /* host-buffer entry point: the inputs only the pointwise chain and the pair loops read arrive on the
      * copy stream while the search runs; the state k_pointwise finalises leaves while the pair loops run */
     if (h->hook_wait_before_pointwise) CU(cudaStreamWaitEvent(st, h->hook_wait_before_pointwise, 0));
-    k_pointwise<<<blocks_for(n, T), T, 0, st>>>(s, v, rho_sorted, use_rho_sorted);
-    launches++;
+    k_pointwise<<<blocks_for(n, T), T, 0, st>>>(s, v, h->rho_sorted, h->kernel_sum_density);
+    h->stage_launches++;
     if (h->hook_after_pointwise) h->hook_after_pointwise(h, h->hook_ctx);
     CU(cudaEventRecord(h->ev[4], st));
 #if TENSORIAL_CORRECTION
-    if (validated) k_correction<LIST_EXACT><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets, h->d_flags);
-    else k_correction<LIST_VALIDATE><<<blocks_for(n_targets, T), T, 0, st>>>(s, v, n_targets, h->d_flags);
-    validated = 1;
-    launches++;
+    if (h->lists_validated) k_correction<LIST_EXACT><<<blocks_for(n, T), T, 0, st>>>(s, v, n, h->d_flags);
+    else k_correction<LIST_VALIDATE><<<blocks_for(n, T), T, 0, st>>>(s, v, n, h->d_flags);
+    h->lists_validated = 1;
+    h->stage_launches++;
 #endif
     CU(cudaEventRecord(h->ev[5], st));
+    return B200SPH_OK;
+}
+
+/* stage 2: pair forces, gravity, end-of-call checks (the one host synchronisation of an evaluation) */
+static int rhs_stage_forces(b200sph_handle *h, const b200sph_view &v, int *offender)
+{
+    cudaStream_t st = h->stream;
+    Sorted &s = h->s;
+    const int n = v.n;
+    int launches = h->stage_launches;
+#if TENSORIAL_CORRECTION
+    if (s.halo_sums_external) {
+        k_import_correction<<<blocks_for(n, 256), 256, 0, st>>>(s, v);
+        launches++;
+    }
+#endif
     const int TF = h->forces_threads;
-    if (validated) k_forces<LIST_EXACT><<<blocks_for(n_targets, TF), TF, h->pad_smem, st>>>(s, v, n_targets, h->d_flags);
-    else k_forces<LIST_VALIDATE><<<blocks_for(n_targets, TF), TF, h->pad_smem, st>>>(s, v, n_targets, h->d_flags);
+    if (h->lists_validated) k_forces<LIST_EXACT><<<blocks_for(n, TF), TF, h->pad_smem, st>>>(s, v, n, h->d_flags);
+    else k_forces<LIST_VALIDATE><<<blocks_for(n, TF), TF, h->pad_smem, st>>>(s, v, n, h->d_flags);
     k_list_stats<<<min(blocks_for(n, 256), h->n_sm * 4), 256, 0, st>>>(s, h->d_flags);
     launches += 2;
     CU(cudaEventRecord(h->ev[6], st));
@@ -1894,9 +1947,10 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     }
     CU(cudaEventRecord(h->ev[7], st));
 
-    int flags[5];
+    int flags[5], aborted = 0;
     CU(cudaMemcpyAsync(flags, h->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&h->h_domain, h->d_domain, sizeof(Domain), cudaMemcpyDeviceToHost, st));
+    if (h->abort_flag) CU(cudaMemcpyAsync(&aborted, h->abort_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
 
@@ -1916,6 +1970,10 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     cudaEventElapsedTime(&S.ms_gravity, h->ev[6], h->ev[7]);
     S.ms_scatter = 0.0f;
 
+    if (aborted) {
+        snprintf(h->err, sizeof(h->err), "evaluation abandoned: the caller's abort flag was set (stale halo plan); no state was modified");
+        return B200SPH_ERR_ABORTED;
+    }
     if (h->h_domain.nonfinite) {
         snprintf(h->err, sizeof(h->err), "non-finite particle coordinate or smoothing length (NaN/Inf) among the %d particles", v.n);
         return B200SPH_ERR_NONFINITE;
@@ -1932,6 +1990,44 @@ extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int
     }
     if (offender) *offender = -1;
     return B200SPH_OK;
+}
+
+extern "C" int b200sph_rhs_eval(b200sph_handle *h, const b200sph_view *view, int *offender)
+{
+    int rc = rhs_check_view(h, view);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    if ((rc = rhs_stage_search(h, *view)) != 0) return rc;
+    if ((rc = rhs_stage_pointwise(h, *view)) != 0) return rc;
+    return rhs_stage_forces(h, *view, offender);
+}
+
+/* The same evaluation in three stream-ordered stages for a multi-GPU host that completes the neighbour SUMS of halo
+ * copies itself: after stage 0 the owners' kernel-sum densities are in view->p.rho, after stage 1
+ * their correction matrices in view->p_rhs.tensorialCorrectionMatrix; the host moves those of the particles it sent
+ * into the matching halo rows of the receivers (stream-ordered, no synchronisation) and goes on.  Stages 0 and 1 only
+ * enqueue work; stage 2 ends with the evaluation's one synchronisation and its checks. */
+extern "C" int b200sph_rhs_eval_stage(b200sph_handle *h, const b200sph_view *view, int stage, int *pending_sum, int *offender)
+{
+    int rc = rhs_check_view(h, view);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    if (pending_sum) *pending_sum = 0;
+    const bool external = h->halo_sums_external && h->n_owned > 0 && h->n_owned < view->n;
+    switch (stage) {
+        case 0:
+            rc = rhs_stage_search(h, *view);
+            if (pending_sum && external && h->kernel_sum_density) *pending_sum = B200SPH_SUM_DENSITY;
+            return rc;
+        case 1:
+            rc = rhs_stage_pointwise(h, *view);
+            if (pending_sum && external && TENSORIAL_CORRECTION) *pending_sum = B200SPH_SUM_CORRECTION;
+            return rc;
+        case 2:
+            return rhs_stage_forces(h, *view, offender);
+        default:
+            return B200SPH_ERR_BAD_ARGUMENT;
+    }
 }
 
 extern "C" int b200sph_export_interactions(b200sph_handle *h, int *interactions, int max_per_row)

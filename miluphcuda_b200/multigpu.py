@@ -40,9 +40,12 @@ from . import api
 HALO_STATE_FIELDS = (
     "x", "y", "z", "vx", "vy", "vz", "m", "h", "h0", "rho", "e", "p", "cs", "materialId",
     "S", "d", "damage_porjutzi", "alpha_jutzi",
+    # the pointwise chain recomputes the damage limit (numActiveFlaws / numFlaws)^(1/DIM) on the copies, exactly as the
+    # owner does (src/damage.cu:33-82); the flaw thresholds themselves stay home (only owners run the flaw scan)
+    "numFlaws", "numActiveFlaws",
 )
-# integer members that must be defined (zero) on halo copies
-HALO_ZERO_FIELDS = ("numFlaws", "numActiveFlaws")
+# neighbour sums of the copies that their owners deliver between the stages of an evaluation
+SUM_FIELDS = {1: ("rho",), 2: ("tensorialCorrectionMatrix",)}
 
 
 class MortonDecomposition:
@@ -203,6 +206,7 @@ class HaloExchange:
         self.last = {}
         self.h_evolves = h_evolves
         self.reuse_plan = reuse_plan
+        self.device_verdict = False   # set by DistributedRhs when the engine carries the plan verdict as its abort flag
         self._plan = None
         self.plan_builds = 0
         self.stale_plans = 0          # evaluations whose plan had gone stale (re-decided before the evaluation ran)
@@ -230,7 +234,9 @@ class HaloExchange:
         dev = f["x"].device
         eng = self.engine
         eng.halo_set_domains(self.boxes, self.box_rank, self.world, self.rank)
-        self._desc = eng.halo_fields(f, self.exchange, self.capacity, HALO_ZERO_FIELDS)
+        self._desc = eng.halo_fields(f, self.exchange, self.capacity)
+        self._sum_desc = {}
+        eng.set_abort_flag(None)
         self.width = eng.halo_row_width(self._desc)
         self._nb_max = max(self.box_counts)
         self._idx = torch.empty(max(self.capacity, 2 * n_owned), dtype=torch.int32, device=dev)
@@ -275,16 +281,45 @@ class HaloExchange:
                           send_counts_dev=i32(send_counts), recv_counts_dev=i32(recv_counts),
                           max_move=max_move, growth=growth, snap=snap)
         self._flag_host.zero_()
+        self._flag.zero_()
+        if self.levels == 2:   # copies that need their own lists are told the plan's margins (reach of a copy to an owned particle)
+            eng.halo_set_list_margin(1.0 + growth, 2.0 * max_move)
         self.plan_builds += 1
 
-    def _check_plan(self, n_owned: int) -> None:
+    def replan(self, n_owned: int) -> None:
+        """The plan went stale: decide again and move the rows again."""
+        self.stale_plans += 1
+        self._build_plan(n_owned)
+        self._move_rows(n_owned)
+
+    def exchange_sums(self, which: int, n_owned: int) -> None:
+        """Deliver the owners' neighbour sums (1: kernel-sum density, 2: tensorial correction matrix) of the particles of
+        the send plan into the receivers' halo rows: the same plan, a row of 1 or DIM*DIM doubles; stream-ordered."""
+        pl, eng = self._plan, self.engine
+        if which not in self._sum_desc:
+            names = [n for n in SUM_FIELDS[which] if n in self.fields]
+            desc = eng.halo_fields(self.fields, names, self.capacity)
+            width = eng.halo_row_width(desc)
+            self._sum_desc[which] = (desc, width)
+        desc, width = self._sum_desc[which]
+        n_send, n_recv, w = pl["n_send"], pl["n_recv"], self.world
+        if self._send.numel() < n_send * width or self._recv.numel() < n_recv * width:
+            raise RuntimeError("neighbour-sum rows are wider than the state rows")
+        send, recv = self._send[: n_send * width], self._recv[: n_recv * width]
+        eng.halo_pack_by_rank(desc, self._idx, pl["send_counts_dev"], w, n_send, send)
+        dist.all_to_all_single(recv, send, output_split_sizes=[c * width for c in pl["recv_counts"]],
+                               input_split_sizes=[c * width for c in pl["send_counts"]], group=self.group)
+        eng.halo_unpack_by_rank(desc, recv, pl["recv_counts_dev"], w, n_recv, n_owned)
+
+    def _check_plan(self, n_owned: int, read_back: bool = True) -> None:
         """Queue the validity check of the current plan (kernel + 4-byte all-reduce + async read-back); no host wait."""
         f, pl = self.fields, self._plan
         sn = pl["snap"]
         self.engine.halo_plan_check(f["x"], f.get("y"), f.get("z"), f["h"], sn["x"], sn.get("y"), sn.get("z"), sn["h"], n_owned,
                                     pl["max_move"], pl["growth"], self._flag)
         dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.group)
-        self._flag_host.copy_(self._flag, non_blocking=True)
+        if read_back:
+            self._flag_host.copy_(self._flag, non_blocking=True)
 
     def invalidate(self) -> None:
         """Drop the plan (the owned set changed, or a check failed): the next run() decides again."""
@@ -311,6 +346,13 @@ class HaloExchange:
         if self._plan is None or self._plan["n_owned"] != n_owned or not self.reuse_plan:
             self._build_plan(n_owned)
             self._move_rows(n_owned)
+        elif self.device_verdict:
+            # The verdict on the plan stays on the device: the all-reduced flag is the evaluation's abort flag
+            # (b200sph_set_abort_flag), every state-modifying kernel reads it first, and a stale plan surfaces as
+            # B200SPH_ERR_ABORTED at the end-of-call synchronisation (DistributedRhs.compute re-decides and repeats).
+            # Nothing here waits for the device.
+            self._check_plan(n_owned, read_back=False)
+            self._move_rows(n_owned)
         else:
             # The verdict on the plan is needed before the evaluation starts (an evaluation mutates state -- p, c_s,
             # S, damage -- so it cannot simply be repeated).  Its 4-byte read-back is queued first and the rows move
@@ -320,9 +362,7 @@ class HaloExchange:
             self._move_rows(n_owned)
             self._flag_event.synchronize()
             if int(self._flag_host[0]) != 0:
-                self.stale_plans += 1
-                self._build_plan(n_owned)
-                self._move_rows(n_owned)
+                self.replan(n_owned)
         pl = self._plan
         self.last = dict(n_halo=pl["n_recv"], sent=pl["n_send"], bytes_sent=pl["n_send"] * self.width * 8, plan_builds=self.plan_builds)
         return n_owned + pl["n_recv"]
@@ -412,9 +452,6 @@ class HaloExchange:
             rows = self._rows(name)
             rows[n_owned: n_owned + n_recv] = recv[:, col: col + w].to(rows.dtype)
             col += w
-        for name in HALO_ZERO_FIELDS:
-            if name in f:
-                self._rows(name)[n_owned: n_owned + n_recv] = 0
         self.last = dict(n_halo=n_recv, sent=n_send, bytes_sent=n_send * self.width * 8)
         return n_owned + n_recv
 
@@ -457,15 +494,23 @@ class DistributedRhs:
     """
 
     def __init__(self, engine: "api.RhsEngine", fields: dict, capacity: int, n_owned: int, dec: MortonDecomposition, meta: dict,
-                 switches: dict, group=None):
+                 switches: dict, group=None, external_sums: bool = True, device_verdict: bool = True):
         self.engine = engine
         self.fields = fields
         self.capacity = capacity
         self.n_owned = n_owned
         self.meta = meta
         h_evolves = bool(switches.get("VARIABLE_SML", 0) or switches.get("INTEGRATE_SML", 0))
-        self.halo = HaloExchange(fields, capacity, dec, levels=halo_levels(switches), group=group, engine=engine,
-                                 h_evolves=h_evolves)
+        on_gpu = fields["x"].device.type == "cuda"
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # GPU buffers: ONE halo level; density / correction matrix of the copies are delivered by their owners between
+        # the stages of the evaluation (neighbour-sum exchange).  CPU tensors (gloo tests, oracle as the evaluator): the
+        # two-level halo, where the evaluator completes those sums itself.
+        self.external_sums = bool(on_gpu and world > 1 and external_sums and halo_levels(switches) == 2)
+        levels = 1 if self.external_sums else halo_levels(switches)
+        self.halo = HaloExchange(fields, capacity, dec, levels=levels, group=group, engine=engine, h_evolves=h_evolves)
+        self.halo.device_verdict = bool(on_gpu and world > 1 and device_verdict)
+        self.sum_exchanges = 0
         self.gravity = GravitySources(dec.dim, group) if meta.get("selfgravity") else None
         self.n_total = n_owned
 
@@ -480,8 +525,32 @@ class DistributedRhs:
         view = api.make_view(self.fields, None, self.n_total, n_real=self.n_total, max_num_flaws=self.meta["max_num_flaws"],
                              selfgravity=self.meta["selfgravity"], theta=self.meta["theta"],
                              grav_const=self.engine.materials.grav_const)
-        self.engine.set_owned(self.n_owned)
-        self.engine.rhs_eval(view)
+        eng = self.engine
+        eng.set_owned(self.n_owned)
+        if self.halo.world == 1 or not (self.external_sums or self.halo.device_verdict):
+            eng.set_halo_sums(False)
+            eng.rhs_eval(view)
+            return
+        eng.set_halo_sums(self.external_sums)
+        if self.halo.device_verdict:
+            eng.set_abort_flag(self.halo._flag)
+        for attempt in range(2):
+            try:
+                for stage in (0, 1, 2):
+                    pending = eng.rhs_eval_stage(view, stage)
+                    if pending:
+                        self.halo.exchange_sums(pending, self.n_owned)
+                        self.sum_exchanges += 1
+                return
+            except api.B200SphError as exc:
+                if exc.code != eng.ERR_ABORTED or attempt == 1:
+                    raise
+                # stale send plan: nothing was modified; decide again (every rank sees the same all-reduced flag)
+                self.halo.replan(self.n_owned)
+                self.n_total = self.n_owned + self.halo._plan["n_recv"]
+                view = api.make_view(self.fields, None, self.n_total, n_real=self.n_total, max_num_flaws=self.meta["max_num_flaws"],
+                                     selfgravity=self.meta["selfgravity"], theta=self.meta["theta"],
+                                     grav_const=eng.materials.grav_const)
 
     def eval(self) -> None:
         self.exchange()

@@ -95,7 +95,7 @@ def test_selection_pack_unpack_match_numpy(config, n, rank, tmp_path):
 
     # --- pack (column-major per rank) and the inverse
     names = [f for f in multigpu.HALO_STATE_FIELDS if f in dev]
-    desc = eng.halo_fields(dev, names, capacity, multigpu.HALO_ZERO_FIELDS)
+    desc = eng.halo_fields(dev, names, capacity)
     width = eng.halo_row_width(desc)
     send = torch.zeros(n_send * width, dtype=torch.float64, device="cuda")
     eng.halo_pack_by_rank(desc, idx, counts, WORLD, n_send, send)
@@ -112,21 +112,18 @@ def test_selection_pack_unpack_match_numpy(config, n, rank, tmp_path):
     # unpack behind the owned rows of a fresh field set that has room for every row
     cap2 = n_owned + n_send
     back = {}
-    for f in list(names) + [z for z in multigpu.HALO_ZERO_FIELDS if z in dev]:
+    for f in list(names):
         per = dev[f].numel() // capacity
         t = torch.full((cap2 * per,), 3, dtype=dev[f].dtype, device="cuda")
         t[: n_owned * per] = dev[f][: n_owned * per]
         back[f] = t
-    desc2 = eng.halo_fields(back, names, cap2, multigpu.HALO_ZERO_FIELDS)
+    desc2 = eng.halo_fields(back, names, cap2)
     eng.halo_unpack_by_rank(desc2, send, counts, WORLD, n_send, n_owned)
     torch.cuda.synchronize()
     for f in names:
         got = back[f].cpu().numpy().reshape(cap2, -1)
         assert np.array_equal(got[n_owned:], local[f].reshape(capacity, -1)[got_idx[:n_send]]), f
         assert np.array_equal(got[:n_owned], local[f].reshape(capacity, -1)[:n_owned]), f"{f}: owned rows were touched"
-    for f in multigpu.HALO_ZERO_FIELDS:
-        if f in back:
-            assert not back[f].cpu().numpy().reshape(cap2, -1)[n_owned:].any(), f
     eng.close()
 
 

@@ -25,7 +25,7 @@ dev = {k: torch.from_numpy(v).cuda() for k, v in arrays.items()}
 boxes, box_rank = dec.all_boxes()
 eng.halo_set_domains(boxes, box_rank, world, rank)
 exchange = [f for f in multigpu.HALO_STATE_FIELDS if f in dev]
-desc = eng.halo_fields(dev, exchange, cap, multigpu.HALO_ZERO_FIELDS)
+desc = eng.halo_fields(dev, exchange, cap)
 width = eng.halo_row_width(desc)
 nb = max(int((box_rank == r).sum()) for r in range(world))
 hmax_mine = torch.zeros(nb, dtype=torch.float64, device="cuda")
