@@ -248,6 +248,17 @@ int b200sph_rk2_step(b200sph_handle *h, const b200sph_view *view, const b200sph_
 int b200sph_rk2_advance(b200sph_handle *h, const b200sph_view *view, const b200sph_particle_arrays rk[3],
                         const b200sph_rk2_params *prm, double t_end, b200sph_rk2_state *state, int *offender);
 
+/* The numbers of conserved_quantities.log (src/io.cu:1661-1838, 1980-2017), summed on the device in one pass instead
+ * of on the host after copying every array back.  Deactivated particles are not counted. */
+typedef struct b200sph_conserved {
+    double mass, e_kin, e_int;
+    double p_abs, p[3];             /* linear momentum */
+    double L_abs, L[3];             /* angular momentum about the origin (2-D: L[0] is the z component, as the reference stores it) */
+    double bary_pos[3], bary_vel[3];
+    int n_ignored;
+} b200sph_conserved;
+int b200sph_conserved_quantities(b200sph_handle *h, const b200sph_view *view, b200sph_conserved *out);
+
 /* Neighbour lists of the last rhs_eval in the caller's indexing, for parity checks and for the
  * reference writer's /number_of_interactions: row i holds noi[i] neighbour ids (unordered).
  * `interactions` is a device buffer of n*max_per_row ints (the reference's dense layout,

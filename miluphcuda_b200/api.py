@@ -107,6 +107,12 @@ class Rk2Params(C.Structure):
     ]
 
 
+class Conserved(C.Structure):
+    _fields_ = [("mass", C.c_double), ("e_kin", C.c_double), ("e_int", C.c_double), ("p_abs", C.c_double), ("p", C.c_double * 3),
+                ("L_abs", C.c_double), ("L", C.c_double * 3), ("bary_pos", C.c_double * 3), ("bary_vel", C.c_double * 3),
+                ("n_ignored", C.c_int)]
+
+
 class Rk2State(C.Structure):
     _fields_ = [
         ("t", C.c_double), ("dt", C.c_double), ("dt_suggested", C.c_double), ("dt_done", C.c_double),
@@ -144,6 +150,7 @@ _EXPORTS = {
     "b200sph_damage_limit": (C.c_int, [C.c_void_p, C.POINTER(View)]),
     "b200sph_init_soundspeed": (C.c_int, [C.c_void_p, C.POINTER(View)]),
     "b200sph_export_interactions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "b200sph_conserved_quantities": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(Conserved)]),
     "b200sph_reorder": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(ParticleArrays), C.c_int, C.c_void_p]),
     "b200sph_rk2_default_params": (C.c_int, [C.POINTER(Rk2Params)]),
     "b200sph_rk2_init": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(ParticleArrays)]),
@@ -375,6 +382,11 @@ class RhsEngine:
 
     def init_soundspeed(self, view: View) -> None:
         self._check(self.lib.b200sph_init_soundspeed(self.handle, C.byref(view)))
+
+    def conserved_quantities(self, view: View) -> Conserved:
+        out = Conserved()
+        self._check(self.lib.b200sph_conserved_quantities(self.handle, C.byref(view), C.byref(out)))
+        return out
 
     def reorder(self, view: View, extra=None, n_extra: int = 0, perm_out=None) -> None:
         """Put the caller's buffers (and `extra`, a C array from rk2_buffers) into search-cell order: new[k] = old[perm[k]]."""

@@ -706,3 +706,98 @@ extern "C" int b200sph_rk2_advance(b200sph_handle *h, const b200sph_view *view, 
     }
     return b200sph_damage_limit(h, view);
 }
+
+/* ------------------------------------------------------------------ conserved quantities on the device
+ * The reference copies the whole particle set to the host before every output and sums mass, energies, linear and
+ * angular momentum and the barycentre there in one thread (src/io.cu:1661-1838) -- the numbers of conserved_quantities.log
+ * (src/io.cu:1980-2017).  Here: one streaming pass, deterministic (fixed block order), 13 sums read back (104 bytes). */
+#define CQ_NV 13
+__global__ void __launch_bounds__(RK_THREADS)
+k_conserved(b200sph_view v, double *partials, unsigned int *counter, double *out)
+{
+    const b200sph_particle_arrays &p = v.p;
+    double a[CQ_NV];
+#pragma unroll
+    for (int k = 0; k < CQ_NV; k++) a[k] = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
+        if (v.p_rhs.materialId[i] == EOS_TYPE_IGNORE) {
+            a[12] += 1.0;
+            continue;
+        }
+        const double m = p.m[i];
+        const double x = p.x[i], vx = p.vx[i];
+        const double y = (DIM > 1) ? p.y[i] : 0.0, vy = (DIM > 1) ? p.vy[i] : 0.0;
+        const double z = (DIM > 2) ? p.z[i] : 0.0, vz = (DIM > 2) ? p.vz[i] : 0.0;
+        a[0] += m;
+        a[1] += m * (vx * vx + vy * vy + vz * vz);
+#if INTEGRATE_ENERGY
+        a[2] += m * p.e[i];
+#endif
+        a[3] += m * vx; a[4] += m * vy; a[5] += m * vz;
+#if DIM == 2
+        a[6] += m * (x * vy - y * vx);
+#elif DIM > 2
+        a[6] += m * (y * vz - z * vy);
+        a[7] += m * (z * vx - x * vz);
+        a[8] += m * (x * vy - y * vx);
+#endif
+        a[9] += m * x; a[10] += m * y; a[11] += m * z;
+    }
+    __shared__ double sh[RK_THREADS / 32][CQ_NV];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < CQ_NV; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < CQ_NV; k++) sh[warp][k] = a[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < CQ_NV; k++) {
+            double t = 0.0;
+            for (int w = 0; w < RK_THREADS / 32; w++) t += sh[w][k];
+            partials[blockIdx.x * CQ_NV + k] = t;
+        }
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last || threadIdx.x >= CQ_NV) return;
+    __threadfence();
+    double t = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; b++) t += __ldcg(partials + b * CQ_NV + threadIdx.x);   /* block order: reproducible */
+    out[threadIdx.x] = t;
+    __syncwarp((1u << CQ_NV) - 1u);
+    if (threadIdx.x == 0) *counter = 0;
+}
+
+extern "C" int b200sph_conserved_quantities(b200sph_handle *h, const b200sph_view *view, b200sph_conserved *out)
+{
+    if (!h || !view || !out || view->n <= 0 || !view->p.x || !view->p.vx || !view->p.m || !view->p_rhs.materialId) return B200SPH_ERR_BAD_ARGUMENT;
+    RCU(cudaSetDevice(h->device));
+    if (rk_scratch(h)) return B200SPH_ERR_CUDA;
+    const int G = min((view->n + RK_THREADS - 1) / RK_THREADS, h->n_sm * 4);
+    double *d_out = (double *)h->rk_scalars;   /* sizeof(RkScalars) >= 13 doubles */
+    static_assert(sizeof(RkScalars) >= CQ_NV * sizeof(double), "scratch too small");
+    static_assert(CQ_NV <= 2 * RK_NRED, "partials are sized for 2 * RK_NRED values per block over 8 n_sm blocks");
+    k_conserved<<<G, RK_THREADS, 0, h->stream>>>(*view, h->rk_partials, h->rk_counter, d_out);
+    double r[CQ_NV];
+    RCU(cudaMemcpyAsync(r, d_out, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+    RCU(cudaStreamSynchronize(h->stream));
+    RCU(cudaGetLastError());
+    out->mass = r[0];
+    out->e_kin = 0.5 * r[1];
+    out->e_int = r[2];
+    for (int k = 0; k < 3; k++) {
+        out->p[k] = r[3 + k];
+        out->L[k] = r[6 + k];
+        out->bary_pos[k] = r[0] > 0.0 ? r[9 + k] / r[0] : 0.0;
+        out->bary_vel[k] = r[0] > 0.0 ? r[3 + k] / r[0] : 0.0;
+    }
+    out->p_abs = sqrt(r[3] * r[3] + r[4] * r[4] + r[5] * r[5]);
+    out->L_abs = sqrt(r[6] * r[6] + r[7] * r[7] + r[8] * r[8]);
+    out->n_ignored = (int)r[12];
+    return B200SPH_OK;
+}

@@ -103,7 +103,7 @@ def run_reference(sc: scenarios.Scenario, workdir: str, env_extra: dict, log_nam
     if decouple:
         cmd += ["-g"]
     if evolve:
-        env_extra = dict(env_extra, REF_EVOLVE="1")
+        env_extra = dict({"REF_EVOLVE": "1"}, **env_extra)   # "pc" from the caller: the predictor-corrector integrator
     env = dict(os.environ)
     env.update(env_extra)
     log = os.path.join(workdir, log_name)
