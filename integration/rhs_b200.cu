@@ -29,6 +29,7 @@
 #include "rhs.h"
 #include "parameter.h"
 #include "pressure.h"
+#include "little_helpers.h"
 
 #define B200SPH_NO_EOS_ENUM
 #include "b200sph.h"
@@ -38,6 +39,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+extern volatile int terminate_flag;
 extern __device__ double gravConst;
 extern __constant__ int isRelaxationRun;
 
@@ -190,6 +192,12 @@ void rightHandSide()
     b200sph_view view;
     int offender = -1, rc, relax = 0;
 
+#if USE_SIGNAL_HANDLER
+    /* SIGINT / SIGTERM: write what there is and leave (src/rhs.cu:170-174, src/little_helpers.cu:33-41) */
+    if (terminate_flag) {
+        copyToHostAndWriteToFile(-2, -2);
+    }
+#endif
     if (!g_b200) b200_init();
     cudaVerify(cudaMemcpyFromSymbol(&bound, p, sizeof(struct Particle)));
     cudaVerify(cudaMemcpyFromSymbol(&relax, isRelaxationRun, sizeof(int)));

@@ -247,7 +247,7 @@ extern "C" int b200sph_set_materials(b200sph_handle *h, const b200sph_materials 
                            eos == EOS_TYPE_TILLOTSON || eos == EOS_TYPE_ISOTHERMAL_GAS || eos == EOS_TYPE_ANEOS ||
                            eos == EOS_TYPE_IDEAL_GAS
 #if PALPHA_POROSITY
-                           || eos == EOS_TYPE_JUTZI || eos == EOS_TYPE_JUTZI_MURNAGHAN
+                           || eos == EOS_TYPE_JUTZI || eos == EOS_TYPE_JUTZI_MURNAGHAN || eos == EOS_TYPE_JUTZI_ANEOS
 #endif
             ;
         if (!known) {
@@ -256,13 +256,13 @@ extern "C" int b200sph_set_materials(b200sph_handle *h, const b200sph_materials 
             return B200SPH_ERR_UNSUPPORTED;
         }
 #if PALPHA_POROSITY
-        if ((eos == EOS_TYPE_JUTZI || eos == EOS_TYPE_JUTZI_MURNAGHAN) && (host[k].crushcurve_style < 0 || host[k].crushcurve_style > 4)) {
+        if ((eos == EOS_TYPE_JUTZI || eos == EOS_TYPE_JUTZI_MURNAGHAN || eos == EOS_TYPE_JUTZI_ANEOS) && (host[k].crushcurve_style < 0 || host[k].crushcurve_style > 4)) {
             snprintf(h->err, sizeof(h->err), "material %d: crushcurve_style = %d is not one of the reference's crush curves 0..4 (src/pressure.cu:365-440)",
                      k, host[k].crushcurve_style);
             return B200SPH_ERR_UNSUPPORTED;
         }
 #endif
-        if (eos == EOS_TYPE_ANEOS && (!mat->aneos_rho || !mat->aneos_e || !mat->aneos_p || !mat->aneos_cs || host[k].aneos_matrix_id < 0)) {
+        if ((eos == EOS_TYPE_ANEOS || eos == EOS_TYPE_JUTZI_ANEOS) && (!mat->aneos_rho || !mat->aneos_e || !mat->aneos_p || !mat->aneos_cs || host[k].aneos_matrix_id < 0)) {
             snprintf(h->err, sizeof(h->err), "material %d: ANEOS tables missing", k);
             return B200SPH_ERR_BAD_ARGUMENT;
         }

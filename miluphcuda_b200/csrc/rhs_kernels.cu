@@ -828,12 +828,39 @@ __device__ inline double eos_pressure(const MatParams &M, double rho, double e, 
         }
 #if PALPHA_POROSITY
         case EOS_TYPE_JUTZI:
+        case EOS_TYPE_JUTZI_ANEOS:
         case EOS_TYPE_JUTZI_MURNAGHAN: {
             /* p = p_solid(alpha rho, e) / alpha with the crush curve alpha(p), src/pressure.cu:204-449 */
             const double al = alpha_in;
             double psolid;
             if (M.eos == EOS_TYPE_JUTZI) {
                 psolid = tillotson_p(M, rho * al, e, true, po.delpdele, po.delpdelrho);
+            } else if (M.eos == EOS_TYPE_JUTZI_ANEOS) {
+                /* tabulated matrix pressure with its slopes (src/pressure.cu:313-363; in-table branch of
+                 * bilinear_interpolation_from_linearized_plus_derivatives, src/aneos.cu:509-531 -- the call site clamps
+                 * the cell indices first, so a point outside the table is extrapolated with the edge cell's slopes) */
+                if (rho <= 0.0) {
+                    psolid = 0.0; po.delpdelrho = 0.0; po.delpdele = 0.0;
+                } else {
+                    const TableCell c = aneos_locate(M, al * rho, e);
+                    if (c.ideal_gas) {
+                        psolid = (M.aneos_gamma - 1.0) * rho * al * e;
+                        po.delpdelrho = (M.aneos_gamma - 1.0) * e;
+                        po.delpdele = (M.aneos_gamma - 1.0) * rho * al;
+                    } else {
+                        const double *t = c_aneos.p + M.aneos_matrix_id;
+                        const double *rt = c_aneos.rho + M.aneos_rho_id, *et = c_aneos.e + M.aneos_e_id;
+                        const int ne = M.aneos_n_e;
+                        const double dxg = rt[c.ix + 1] - rt[c.ix], dyg = et[c.iy + 1] - et[c.iy];
+                        const double delta_x = c.nx * dxg, delta_y = c.ny * dyg;
+                        const double k_a = (t[(c.ix + 1) * ne + c.iy] - t[c.ix * ne + c.iy]) / dxg;
+                        const double k_b = (t[(c.ix + 1) * ne + c.iy + 1] - t[c.ix * ne + c.iy + 1]) / dxg;
+                        const double a2 = t[c.ix * ne + c.iy] + delta_x * k_a, b2 = t[c.ix * ne + c.iy + 1] + delta_x * k_b;
+                        po.delpdelrho = k_a + delta_y * (k_b - k_a) / dyg;
+                        po.delpdele = (b2 - a2) / dyg;
+                        psolid = a2 + delta_y * po.delpdele;
+                    }
+                }
             } else {
                 const double eta = rho * al / M.rho0;
                 po.delpdele = 0.0;
@@ -933,7 +960,7 @@ k_pointwise(Sorted s, b200sph_view v, const double *rho_sorted, int use_rho_sort
     double pres = eos_ignored ? p.p[i] : eos_pressure(M, rho, e, cs, alpha_in, po);
 #if PALPHA_POROSITY
     if (eos_ignored) {
-    } else if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN) {
+    } else if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN || M.eos == EOS_TYPE_JUTZI_ANEOS) {
         p.dalphadp[i] = po.dalphadp;
         p.dalphadrho[i] = po.dalphadrho;
         p.f[i] = po.f;
@@ -1736,7 +1763,7 @@ __global__ void k_pressure_only(b200sph_view v)
     PorousOut po;
     double pres = eos_pressure(M, p.rho[i], p.e ? p.e[i] : 0.0, p.cs[i], alpha_in, po);
 #if PALPHA_POROSITY
-    if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN) {
+    if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN || M.eos == EOS_TYPE_JUTZI_ANEOS) {
         p.dalphadp[i] = po.dalphadp;
         p.dalphadrho[i] = po.dalphadrho;
         p.f[i] = po.f;

@@ -25,6 +25,7 @@ CONFIG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs")
 CONFIG_NAMES = ("shocktube", "sedov", "rings", "impact", "giant_hydro", "giant_solid", "nakamura")
 # scenario variants that run on another config's switch set (library)
 VARIANT_CONFIG = {"giant_aneos": "giant_hydro", "sedov_ignore": "sedov", "impact_ignore": "impact", "giant_ignore": "giant_hydro",
+                  "impact_aneos": "impact",
                   "impact_crush1": "impact", "impact_crush2": "impact", "impact_crush3": "impact", "impact_crush4": "impact"}
 
 
@@ -341,14 +342,26 @@ def impact(n_target: int = 58402, seed: int = 20240229) -> Scenario:
     shell = 2.0 * np.pi * rr**2  # half sphere
     eff_vol = np.trapezoid(shell * keep_fraction(rr), rr)
     delta = (eff_vol / n_target) ** (1.0 / 3.0)
-    pts = _lattice([-R, -R, -R], [R + delta, R + delta, 0.5 * delta], delta, 3)
-    pts = pts + 0.5 * delta * np.array([0.37, 0.41, -1.0])  # lattice not aligned with cell planes
-    r = np.sqrt((pts**2).sum(axis=1))
-    sel = (r < R) & (pts[:, 2] <= 0.0)
-    pts, r = pts[sel], r[sel]
-    frac = keep_fraction(r)
-    kept = rng.random(pts.shape[0]) < frac
-    pts, frac = pts[kept], frac[kept]
+    # the lattice of the bounding box is walked in slabs of x-planes (x is its slowest index, so the point order -- and with
+    # it every random draw -- is that of the whole lattice at once, which needs > 60 GB at 8M particles)
+    xs = np.arange(-R, R + delta, delta)
+    ys = np.arange(-R, R + delta, delta)
+    zs = np.arange(-R, 0.5 * delta, delta)
+    shift = 0.5 * delta * np.array([0.37, 0.41, -1.0])  # lattice not aligned with cell planes
+    slab = max(1, int(4.0e6 / (len(ys) * len(zs))))
+    pts_list, frac_list = [], []
+    for i0 in range(0, len(xs), slab):
+        g = np.meshgrid(xs[i0: i0 + slab], ys, zs, indexing="ij")
+        chunk = np.stack([a.ravel() for a in g], axis=1) + shift
+        r = np.sqrt((chunk**2).sum(axis=1))
+        sel = (r < R) & (chunk[:, 2] <= 0.0)
+        chunk, r = chunk[sel], r[sel]
+        f = keep_fraction(r)
+        kept = rng.random(chunk.shape[0]) < f
+        pts_list.append(chunk[kept])
+        frac_list.append(f[kept])
+    pts, frac = np.concatenate(pts_list), np.concatenate(frac_list)
+    del pts_list, frac_list
     vol = delta**3 / frac
     # projectile: sphere radius 0.5 at (1.5, 0, 2.598) moving with (-3000, 0, -5196.15)
     pc = np.array([1.5, 0.0, 2.598])
@@ -516,7 +529,9 @@ def _giant_cfg(sml: float) -> str:
 # outer loop) is synthesised from a Tillotson-like closed form.  The grid is deliberately narrower than the
 # particle states so that every branch of the lookup runs: rho below / above the table (edge-cell
 # extrapolation), e below the table (clamped) and e above it (ideal-gas fallback, src/pressure.cu / aneos.cu).
+_ANEOS_PARAMS_BASALT = dict(rho0=2700.0, A=2.67e10, B=2.67e10, E0=4.87e8, a=0.5, b=1.5, bulk_cs=3144.0)
 _ANEOS_PARAMS = {
+    "basalt": _ANEOS_PARAMS_BASALT,
     "iron": dict(rho0=7800.0, A=1.28e11, B=1.05e11, E0=9.5e6, a=0.5, b=1.5, bulk_cs=4050.0),
     "granite": dict(rho0=2680.0, A=1.8e10, B=1.8e10, E0=1.6e7, a=0.5, b=1.3, bulk_cs=2590.0),
 }
@@ -692,6 +707,20 @@ def with_ignored_material(sc: Scenario) -> Scenario:
     return sc
 
 
+def with_tabulated_matrix(sc: Scenario) -> Scenario:
+    """The impact scenario with the p-alpha model on a TABULATED matrix EOS (eos.type = 13, EOS_TYPE_JUTZI_ANEOS;
+    reference: src/pressure.cu:313-363, src/soundspeed.cu:167-206): the Tillotson keys give way to a synthetic
+    ANEOS-format table, narrower than the particle states so that the edge-cell extrapolation, the cold-curve clamp and
+    the ideal-gas fallback of the lookup all run."""
+    q = _ANEOS_PARAMS["basalt"]
+    cfg = sc.material_cfg.replace("type = 5", "type = 13")
+    cfg = cfg.replace("till_rho_0 = 2.7e3", f"table_path = \"basalt.aneos.table\"\n      n_rho = {ANEOS_N_RHO}\n      n_e = {ANEOS_N_E}\n"
+                      f"      aneos_rho_0 = {q['rho0']}\n      aneos_bulk_cs = {q['bulk_cs']}\n      aneos_gamma = 1.4\n      till_rho_0 = 2.7e3")
+    sc.material_cfg = cfg
+    sc.includes = dict(sc.includes, **{"basalt.aneos.table": aneos_table_text("basalt")})
+    return sc
+
+
 def with_crush_curve(sc: Scenario, style: int) -> Scenario:
     """The impact scenario on another crush curve of the p-alpha model (reference: src/pressure.cu:365-440)."""
     extra = f"crushcurve_style = {style}"
@@ -704,7 +733,7 @@ def with_crush_curve(sc: Scenario, style: int) -> Scenario:
 
 def make(config: str, n: int | None = None, stirred: bool = False) -> Scenario:
     """Scenario by config name at roughly n particles (None = the shipped resolution)."""
-    if stirred and not (config.endswith("_ignore") or config.startswith("impact_crush")):   # those variants are stirred already
+    if stirred and not (config.endswith("_ignore") or config.startswith("impact_crush") or config == "impact_aneos"):   # those variants are stirred already
         return stir(make(config, n))
     if config == "shocktube":
         return shocktube() if n is None else shocktube(dx=5e-4 * 3376.0 / n)
@@ -724,6 +753,8 @@ def make(config: str, n: int | None = None, stirred: bool = False) -> Scenario:
         return nakamura() if n is None else nakamura(n_target=n)
     if config.endswith("_ignore"):
         return with_ignored_material(stir(make({"giant_ignore": "giant_hydro"}.get(config, config[:-7]), n)))
+    if config == "impact_aneos":
+        return with_tabulated_matrix(stir(make("impact", n)))
     if config.startswith("impact_crush"):
         return with_crush_curve(stir(make("impact", n)), int(config[-1]))
     raise ValueError(f"unknown config {config!r}")

@@ -39,7 +39,7 @@ GOLDEN_N = {"shocktube": None, "sedov": 2500, "rings": 2500, "impact": 2500, "gi
 # variants that exist in one flavour only (already stirred): deactivated particles (both the eos.type = IGNORE material and
 # materialId = -1 set by the hook), the other crush curves of the p-alpha model
 GOLDEN_SINGLE = {"sedov_ignore": 2500, "impact_ignore": 2500, "giant_ignore": 2500,
-                 "impact_crush1": 1500, "impact_crush2": 1500, "impact_crush3": 1500, "impact_crush4": 1500}
+                 "impact_aneos": 1500, "impact_crush1": 1500, "impact_crush2": 1500, "impact_crush3": 1500, "impact_crush4": 1500}
 DEACTIVATE_STRIDE = 13
 
 # Evolved states ("a state after >= 20 accepted steps"): the reference's own rk2_adaptive integrates the
