@@ -188,6 +188,47 @@ def time_oracle_port(workload: str, n: int, budget_s: float = 15.0):
     return value, cores, sample, dt / calls * 1e3
 
 
+class NativeDistributedRhs:
+    """bench.py's view of the C++/NCCL host (csrc/mg.cu): decompose + migrate once, then one b200sph_mg_rhs_eval per step."""
+
+    def __init__(self, api, torch, dist, workload, eng, dev, capacity, n, meta, mine, rank, world):
+        import types
+        self.api, self.eng, self.dev, self.capacity, self.meta = api, eng, dev, capacity, meta
+        ids = [api.NativeMultiGpu.unique_id(workload) if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        self.mg = api.NativeMultiGpu(eng, rank, world, ids[0])
+        self.ids = torch.zeros(capacity, dtype=torch.int32, device="cuda")   # global ids ride along as an extra member
+        self.ids[:n] = torch.as_tensor(mine, dtype=torch.int32, device="cuda")
+        extra = eng.rk2_buffers([{"depth": self.ids}, {}, {}])
+        view = self._view(n)
+        self.mg.decompose(view, n)
+        self.n_owned = self.mg.migrate(view, n, capacity, extra, 1)
+        self.n_total = self.n_owned
+        self.external_sums, self.sum_exchanges = True, 0
+        self.halo = types.SimpleNamespace(levels=1, SKIN=0.15, plan_builds=0, stale_plans=0, device_verdict=True, last={})
+
+    def _view(self, n):
+        m = self.meta
+        return self.api.make_view(self.dev, None, n, max_num_flaws=m["max_num_flaws"], selfgravity=m["selfgravity"], theta=m["theta"],
+                                  grav_const=self.eng.materials.grav_const)
+
+    def global_ids(self):
+        return self.ids[: self.n_owned].cpu().numpy().astype("int64")
+
+    def exchange(self):
+        pass   # exchange and evaluation are one C call
+
+    def compute(self):
+        self.n_total = self.mg.rhs_eval(self._view(self.n_owned), self.n_owned, self.capacity)
+        st = self.mg.stats()
+        self.sum_exchanges = st["sum_exchanges"]
+        self.halo.plan_builds, self.halo.stale_plans = st["plan_builds"], st["stale_plans"]
+        self.halo.last = {"bytes_sent": st["halo_bytes_sent"]}
+
+    def eval(self):
+        self.compute()
+
+
 def single_domain_check(api, torch, dist, multigpu, workload, cfg, full, meta, sc, M, rank, world, local_rank) -> dict:
     """Rank 0 evaluates the WHOLE particle set as one domain on its GPU and sends every rank the rows it owns; each rank
     compares them with what the distributed evaluation left in its buffers."""
@@ -258,6 +299,9 @@ def main() -> None:
     ap.add_argument("--particles", type=int, default=None, help="particles per GPU (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mg-host", default="python", choices=["python", "native"],
+                    help="several GPUs: host layer of the exchange -- miluphcuda_b200/multigpu.py over torch.distributed, or the C++/NCCL "
+                         "host behind the C-ABI (csrc/mg.cu, b200sph_mg_*)")
     ap.add_argument("--halo-headroom", type=float, default=1.6, help="capacity of a rank's buffers over its owned particles")
     ap.add_argument("--no-parity-check", action="store_true", help="several GPUs: skip the single-domain comparison after the timed region")
     ap.add_argument("--no-reorder", action="store_true", help="keep the generator's particle order (no b200sph_reorder)")
@@ -333,14 +377,23 @@ def main() -> None:
             engines[capacity].set_stream(stream.cuda_stream)
         eng = engines[capacity]
         dev = {k: torch.from_numpy(v).cuda() for k, v in arrays.items()}
-        drhs = multigpu.DistributedRhs(eng, dev, capacity, n, dec, meta, sc.switches())
-        if world == 1 and not args.no_reorder:
+        native = world > 1 and args.mg_host == "native"
+        drhs = None if native else multigpu.DistributedRhs(eng, dev, capacity, n, dec, meta, sc.switches())
+        if not args.no_reorder:
             # persistent cell order: the product's own b200sph_reorder(), once, before anything is timed
-            # -- what an integrator does every few hundred steps; the host copies follow so that e2e uploads that order
+            # -- what an integrator does every few hundred steps (on several GPUs: every rank for the particles it owns);
+            # the host copies follow so that e2e uploads that order
             view0 = api.make_view(dev, None, n, max_num_flaws=meta["max_num_flaws"], selfgravity=meta["selfgravity"],
                                   theta=meta["theta"], grav_const=eng.materials.grav_const)
-            eng.reorder(view0)
+            perm = torch.empty(n, dtype=torch.int32, device="cuda")
+            eng.set_owned(0)
+            eng.reorder(view0, perm_out=perm)
+            mine = np.asarray(mine)[perm.cpu().numpy()]
             arrays = {k: v.cpu().numpy() for k, v in dev.items()}
+        if native:
+            drhs = NativeDistributedRhs(api, torch, dist, workload, eng, dev, capacity, n, meta, mine, rank, world)
+            n, mine = drhs.n_owned, drhs.global_ids()
+            arrays = {k: v.cpu().numpy() for k, v in dev.items()}   # the rows a rank holds changed with the migration
         for _ in range(args.warmup):
             drhs.eval()
         barrier()
@@ -514,11 +567,14 @@ def main() -> None:
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_label(workload, n_global, n_global // world, state_kind, evolved_steps),
                    "state": state_kind, "state_note": state_note,
-                   "particle_order": ("generator order (as the reference arm)" if (args.no_reorder or world > 1) else
+                   "particle_order": ("generator order (as the reference arm)" if args.no_reorder else
                                       "search-cell order: b200sph_reorder() applied once before the timed region (SURVEY 8f row 2); "
                                       "the reference keeps the input file's order"), "particles_per_gpu": n_global // world, "particles": int(total_particles),
                    "mean_interactions": total_noi / n, "l2": "512 MiB buffer written between timed steps (untimed)",
                    "timing": "per-step CUDA events on the launching stream, summed over K steps, max over ranks",
+                   "multi_gpu_host": (("C++ over NCCL behind the C-ABI (csrc/mg.cu: b200sph_mg_decompose / migrate / rhs_eval)"
+                                       if args.mg_host == "native" else "Python over torch.distributed (miluphcuda_b200/multigpu.py)")
+                                      if world > 1 else None),
                    "multi_gpu": ("Morton-curve domain decomposition, %d-level state halo per evaluation (NCCL all_to_all of the packed "
                                  "state)%s; the send plan is reused while no particle moved > %.2f h_min, its verdict %s: "
                                  "%d plan builds, %d stale plans in this run%s"

@@ -359,6 +359,32 @@ int b200sph_halo_set_list_margin(b200sph_handle *h, double reach_scale, double s
 int b200sph_set_gravity_sources(b200sph_handle *h, const double *x, const double *y, const double *z, const double *m,
                                 int n_sources, int own_begin);
 
+/* ---- the multi-GPU host behind the C-ABI (csrc/mg.cu): one b200sph_mg per GPU/process, NCCL bound at run time.
+ * A C host that holds a particle set spread over the GPUs of one box calls
+ *     rank 0: b200sph_mg_unique_id(id)  -> hands the 128 bytes to every rank (MPI_Bcast, a file, ...)
+ *     all   : b200sph_mg_create(&mg, handle, rank, world, id)
+ *             b200sph_mg_decompose(mg, view, n_held, by_work)   Morton-curve domains of equal count / equal sum(noi)
+ *             b200sph_mg_migrate(mg, view, rk, 3, n_held, capacity, &n_owned)   records move to their owners
+ *     per rightHandSide():
+ *             b200sph_mg_rhs_eval(mg, view, n_owned, capacity, &n_total, &offender)
+ * and repeats decompose + migrate every few hundred steps, at a step boundary (the halo plan tolerates a drift of
+ * 0.15 h_min out of the own boxes, no more).  All arrays of `view` (and of the extra buffers) have room for `capacity`
+ * rows; rows [0, n_owned) are the rank's own particles, the halo copies are written behind them. ---- */
+typedef struct b200sph_mg b200sph_mg;
+typedef struct b200sph_mg_stats {
+    int n_boxes, n_halo, plan_builds, stale_plans, sum_exchanges;
+    long long migrated_out, migrated_in, halo_bytes_sent;
+} b200sph_mg_stats;
+int b200sph_mg_unique_id(void *id128, char *err, size_t errlen);
+int b200sph_mg_create(b200sph_mg **out, b200sph_handle *h, int rank, int world, const void *id128);
+int b200sph_mg_destroy(b200sph_mg *mg);
+const char *b200sph_mg_last_error(const b200sph_mg *mg);
+int b200sph_mg_decompose(b200sph_mg *mg, const b200sph_view *view, int n_held, int weight_by_interactions);
+int b200sph_mg_migrate(b200sph_mg *mg, const b200sph_view *view, const b200sph_particle_arrays *extra, int n_extra, int n_held,
+                       int capacity, int *n_held_out);
+int b200sph_mg_rhs_eval(b200sph_mg *mg, const b200sph_view *view, int n_owned, int capacity, int *n_total_out, int *offender);
+int b200sph_mg_get_stats(const b200sph_mg *mg, b200sph_mg_stats *out);
+
 #ifdef __cplusplus
 }
 #endif

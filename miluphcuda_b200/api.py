@@ -107,6 +107,11 @@ class Rk2Params(C.Structure):
     ]
 
 
+class MgStats(C.Structure):
+    _fields_ = [("n_boxes", C.c_int), ("n_halo", C.c_int), ("plan_builds", C.c_int), ("stale_plans", C.c_int), ("sum_exchanges", C.c_int),
+                ("migrated_out", C.c_longlong), ("migrated_in", C.c_longlong), ("halo_bytes_sent", C.c_longlong)]
+
+
 class Conserved(C.Structure):
     _fields_ = [("mass", C.c_double), ("e_kin", C.c_double), ("e_int", C.c_double), ("p_abs", C.c_double), ("p", C.c_double * 3),
                 ("L_abs", C.c_double), ("L", C.c_double * 3), ("bary_pos", C.c_double * 3), ("bary_vel", C.c_double * 3),
@@ -150,6 +155,14 @@ _EXPORTS = {
     "b200sph_damage_limit": (C.c_int, [C.c_void_p, C.POINTER(View)]),
     "b200sph_init_soundspeed": (C.c_int, [C.c_void_p, C.POINTER(View)]),
     "b200sph_export_interactions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "b200sph_mg_unique_id": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "b200sph_mg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "b200sph_mg_destroy": (C.c_int, [C.c_void_p]),
+    "b200sph_mg_last_error": (C.c_char_p, [C.c_void_p]),
+    "b200sph_mg_decompose": (C.c_int, [C.c_void_p, C.POINTER(View), C.c_int, C.c_int]),
+    "b200sph_mg_migrate": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(ParticleArrays), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "b200sph_mg_rhs_eval": (C.c_int, [C.c_void_p, C.POINTER(View), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200sph_mg_get_stats": (C.c_int, [C.c_void_p, C.POINTER(MgStats)]),
     "b200sph_conserved_quantities": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(Conserved)]),
     "b200sph_reorder": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(ParticleArrays), C.c_int, C.c_void_p]),
     "b200sph_rk2_default_params": (C.c_int, [C.POINTER(Rk2Params)]),
@@ -509,3 +522,55 @@ class RhsEngine:
             self.close()
         except Exception:
             pass
+
+
+class NativeMultiGpu:
+    """The multi-GPU host of csrc/mg.cu (C++ over NCCL) seen from Python: what a C host calls, one object per rank."""
+
+    def __init__(self, engine: RhsEngine, rank: int, world: int, unique_id: bytes):
+        self.engine, self.lib = engine, engine.lib
+        self.handle = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        rc = self.lib.b200sph_mg_create(C.byref(self.handle), engine.handle, rank, world, buf)
+        if rc != 0:
+            raise B200SphError(rc, self._error())
+
+    @staticmethod
+    def unique_id(config: str) -> bytes:
+        lib = load_library(config)
+        buf, err = C.create_string_buffer(128), C.create_string_buffer(512)
+        rc = lib.b200sph_mg_unique_id(buf, err, len(err))
+        if rc != 0:
+            raise B200SphError(rc, err.value.decode(errors="replace"))
+        return buf.raw
+
+    def _error(self) -> str:
+        msg = self.lib.b200sph_mg_last_error(self.handle) if self.handle else b""
+        return (msg or b"").decode(errors="replace") or self.lib.b200sph_last_error(self.engine.handle).decode(errors="replace")
+
+    def _check(self, rc: int, offender: int = -1) -> None:
+        if rc != 0:
+            raise B200SphError(rc, self._error(), offender)
+
+    def decompose(self, view: View, n_held: int, by_work: bool = False) -> None:
+        self._check(self.lib.b200sph_mg_decompose(self.handle, C.byref(view), n_held, int(by_work)))
+
+    def migrate(self, view: View, n_held: int, capacity: int, extra=None, n_extra: int = 0) -> int:
+        out = C.c_int(0)
+        self._check(self.lib.b200sph_mg_migrate(self.handle, C.byref(view), extra, n_extra, n_held, capacity, C.byref(out)))
+        return out.value
+
+    def rhs_eval(self, view: View, n_owned: int, capacity: int) -> int:
+        n_total, off = C.c_int(0), C.c_int(-1)
+        self._check(self.lib.b200sph_mg_rhs_eval(self.handle, C.byref(view), n_owned, capacity, C.byref(n_total), C.byref(off)), off.value)
+        return n_total.value
+
+    def stats(self) -> dict:
+        st = MgStats()
+        self._check(self.lib.b200sph_mg_get_stats(self.handle, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.b200sph_mg_destroy(self.handle)
+            self.handle = C.c_void_p()

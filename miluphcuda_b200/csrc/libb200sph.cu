@@ -9,4 +9,5 @@
 #include "gravity.cu"
 #include "halo.cu"
 #include "integrate.cu"
+#include "mg.cu"
 #include "capi.cu"
