@@ -229,16 +229,51 @@ class NativeDistributedRhs:
         self.compute()
 
 
-def single_domain_check(api, torch, dist, multigpu, workload, cfg, full, meta, sc, M, rank, world, local_rank) -> dict:
-    """Rank 0 evaluates the WHOLE particle set as one domain on its GPU and sends every rank the rows it owns; each rank
-    compares them with what the distributed evaluation left in its buffers."""
+def _perturb(torch, dev, n, ids, amp_v, amp_e, integrate_density):
+    """Deterministic perturbation keyed by the GLOBAL particle id (the same on whichever rank and row a particle lives):
+    velocities, energy and density move so that every pair term of the rates is exercised on the pristine lattices."""
+    ph = ids.to(torch.float64)
+    for k, name in enumerate(("vx", "vy", "vz")):
+        if name in dev:
+            dev[name][:n] += amp_v * torch.sin(0.37 * (k + 1) * ph + k)
+    if "e" in dev:
+        dev["e"][:n] += amp_e * (1.0 + torch.sin(0.53 * ph))
+    if integrate_density:
+        dev["rho"][:n] *= 1.0 + 0.02 * torch.sin(0.29 * ph)
+
+
+def single_domain_check(api, torch, dist, workload, cfg, full, meta, sc, M, rank, world, local_rank) -> dict:
+    """Correctness of the distributed evaluation at the size it was timed at.  Every particle gets a deterministic
+    perturbation keyed by its global id (on the pristine step-0 lattices most rates vanish: a comparison of zeros proves
+    little); the distributed buffers are evaluated twice more; rank 0 evaluates the WHOLE particle set as one domain on
+    its own GPU through the same sequence and sends every rank the rows it owns; each rank compares."""
     import numpy as np
     names_all = ("ax", "ay", "az", "drhodt", "dedt", "dhdt", "dSdt", "dddt", "dalphadt", "rho", "p", "cs", "g_ax", "g_ay", "g_az", "noi")
-    n, cap, dev = M["n"], M["capacity"], M["dev"]
+    n, cap, dev, drhs = M["n"], M["capacity"], M["dev"], M["drhs"]
     names = [f for f in names_all if f in dev]
     n_all = sc.n
-    want, scales = {}, {}
+    integrate_density = bool(sc.switches().get("INTEGRATE_DENSITY", 0))
+    ids = torch.as_tensor(np.asarray(M["mine"]), dtype=torch.int64, device="cuda")
+    # every rank's global ids, in its row order, to rank 0
+    counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+    counts[rank] = n
+    dist.all_reduce(counts)
+    counts = [int(c) for c in counts.tolist()]
+    amps = torch.zeros(2, dtype=torch.float64, device="cuda")
     if rank == 0:
+        cs_mean = float(dev["cs"][:n].mean().item())
+        amps[0], amps[1] = 0.05 * cs_mean, 0.01 * cs_mean * cs_mean
+    dist.broadcast(amps, src=0)
+    amp_v, amp_e = float(amps[0].item()), float(amps[1].item())
+    _perturb(torch, dev, n, ids, amp_v, amp_e, integrate_density)
+    for _ in range(2):
+        drhs.eval()
+    torch.cuda.synchronize()
+    want = {}
+    if rank == 0:
+        all_ids = [ids] + [torch.empty(counts[r], dtype=torch.int64, device="cuda") for r in range(1, world)]
+        for r in range(1, world):
+            dist.recv(all_ids[r], src=r)
         eng1 = api.RhsEngine(workload, n_max=n_all, device=local_rank, material_cfg=cfg)
         eng1.set_stream(torch.cuda.current_stream().cuda_stream)
         dev1 = {k: torch.from_numpy(v).cuda() for k, v in full.items()}
@@ -246,15 +281,15 @@ def single_domain_check(api, torch, dist, multigpu, workload, cfg, full, meta, s
                               grav_const=eng1.materials.grav_const)
         for _ in range(3):   # like the timed buffers: evaluated repeatedly, so that c_s has seen its own pressure
             eng1.rhs_eval(view1)
+        _perturb(torch, dev1, n_all, torch.arange(n_all, dtype=torch.int64, device="cuda"), amp_v, amp_e, integrate_density)
+        for _ in range(2):
+            eng1.rhs_eval(view1)
         torch.cuda.synchronize()
-        x = np.stack([full[a][:n_all] for a in ["x", "y", "z"][: sc.dim]], axis=1)
-        _, parts = multigpu.morton_partition(x, world)
         sc_t = torch.tensor([float(torch.sqrt(torch.mean(dev1[f].double() ** 2)).item()) for f in names], dtype=torch.float64, device="cuda")
         for r in range(world):
-            idx = torch.from_numpy(parts[r]).cuda()
             for f in names:
                 per = dev1[f].numel() // n_all
-                rows = dev1[f].view(n_all, per)[idx].double().contiguous()
+                rows = dev1[f].view(n_all, per)[all_ids[r]].double().contiguous()
                 if r == 0:
                     want[f] = rows
                 else:
@@ -262,6 +297,7 @@ def single_domain_check(api, torch, dist, multigpu, workload, cfg, full, meta, s
         eng1.close()
         del dev1
     else:
+        dist.send(ids, dst=0)
         sc_t = torch.empty(len(names), dtype=torch.float64, device="cuda")
         for f in names:
             per = dev[f].numel() // cap
@@ -269,7 +305,7 @@ def single_domain_check(api, torch, dist, multigpu, workload, cfg, full, meta, s
             dist.recv(buf, src=0)
             want[f] = buf
     dist.broadcast(sc_t, src=0)
-    worst, worst_name = 0.0, None
+    worst, worst_name, nonzero = 0.0, None, 0
     for k, f in enumerate(names):
         if f == "noi":
             continue
@@ -278,13 +314,15 @@ def single_domain_check(api, torch, dist, multigpu, workload, cfg, full, meta, s
         denom = torch.clamp(want[f].abs(), min=float(sc_t[k].item()))
         denom = torch.where(denom > 0, denom, torch.ones_like(denom))
         err = float(((got - want[f]).abs() / denom).max().item())
+        nonzero += int(float(sc_t[k].item()) > 0.0)
         if err > worst:
             worst, worst_name = err, f
     noi_bad = int((dev["noi"][:n].double() != want["noi"].view(-1)).sum().item())
     torch.cuda.empty_cache()
-    return {"what": "owned particles of every rank vs a single-domain evaluation of all %d particles (rank 0's GPU)" % n_all,
-            "fields": [f for f in names if f != "noi"], "max_rel_err": worst, "worst_field": worst_name, "noi_mismatches": noi_bad,
-            "tolerance": 1e-9}
+    return {"what": ("owned particles of every rank vs a single-domain evaluation of all %d particles (rank 0's GPU), on a state "
+                     "perturbed per global particle id so that every rate is non-zero" % n_all),
+            "fields": [f for f in names if f != "noi"], "fields_nonzero": nonzero, "max_rel_err": worst, "worst_field": worst_name,
+            "noi_mismatches": noi_bad, "tolerance": 1e-9}
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -450,7 +488,7 @@ def main() -> None:
     # rank's own GPU (after the timed region): neighbour counts of the owned particles equal, every rate within 1e-9
     parity = None
     if world > 1 and not args.no_parity_check:
-        parity = single_domain_check(api, torch, dist, multigpu, workload, cfg, full_timed if rank == 0 else None, meta, sc, M,
+        parity = single_domain_check(api, torch, dist, workload, cfg, full_timed if rank == 0 else None, meta, sc, M,
                                      rank, world, local_rank)
         worst = torch.tensor([parity["max_rel_err"], float(parity["noi_mismatches"])], dtype=torch.float64, device="cuda")
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)

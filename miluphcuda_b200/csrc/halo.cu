@@ -361,7 +361,7 @@ extern "C" int b200sph_halo_plan_check(b200sph_handle *h, const double *x, const
 }
 
 /* ------------------------------------------------------------------ pack / unpack */
-#define HALO_MAX_FIELDS 40
+#define HALO_MAX_FIELDS 96
 struct HaloFields {
     void *data[HALO_MAX_FIELDS];
     int per[HALO_MAX_FIELDS];       /* values per particle */

@@ -500,15 +500,34 @@ extern "C" int b200sph_mg_migrate(b200sph_mg *mg, const b200sph_view *view, cons
     sets.push_back(view->p);
     sets.push_back(view->p_rhs);
     for (int k = 0; k < n_extra; k++) sets.push_back(extra[k]);
-    b200sph_halo_field fields[4 * 64];
-    const int nf = mg_all_fields(sets.data(), (int)sets.size(), view->max_num_flaws, fields, 4 * 64);
-    const int width = b200sph_halo_row_width(fields, nf);
-    if (mg_grow(mg, &mg->d_send, &mg->send_cap, (size_t)n_out * width)) return B200SPH_ERR_CUDA;
-    if (mg_grow(mg, &mg->d_recv, &mg->recv_cap, (size_t)n_in * width)) return B200SPH_ERR_CUDA;
+    b200sph_halo_field fields[6 * 64];
+    const int nf = mg_all_fields(sets.data(), (int)sets.size(), view->max_num_flaws, fields, 6 * 64);
     MCU(cudaMemcpyAsync(mg->d_send_counts, sc.data(), W * sizeof(int), cudaMemcpyHostToDevice, st));
     MCU(cudaMemcpyAsync(mg->d_recv_counts, rc.data(), W * sizeof(int), cudaMemcpyHostToDevice, st));
-    if (n_out > 0) MRC(b200sph_halo_pack_by_rank(h, fields, nf, mg->d_order, mg->d_send_counts, W, n_out, mg->d_send));
-    if (mg_exchange_rows(mg, mg->d_send, mg->d_recv, sc, rc, width)) return B200SPH_ERR_CUDA;
+    /* the members travel in groups of at most MG_FIELD_GROUP (the pack kernels take their member table by value);
+     * every group is packed and sent before anything is overwritten, its arrivals wait in their own buffer */
+    const int MG_FIELD_GROUP = 64;
+    const int n_groups = (nf + MG_FIELD_GROUP - 1) / MG_FIELD_GROUP;
+    std::vector<int> g_width(n_groups), g_first(n_groups), g_count(n_groups);
+    size_t recv_total = 0, send_max = 0;
+    for (int g = 0; g < n_groups; g++) {
+        g_first[g] = g * MG_FIELD_GROUP;
+        g_count[g] = std::min(MG_FIELD_GROUP, nf - g_first[g]);
+        g_width[g] = b200sph_halo_row_width(fields + g_first[g], g_count[g]);
+        recv_total += (size_t)n_in * g_width[g];
+        send_max = std::max(send_max, (size_t)n_out * g_width[g]);
+    }
+    if (mg_grow(mg, &mg->d_send, &mg->send_cap, send_max)) return B200SPH_ERR_CUDA;
+    if (mg_grow(mg, &mg->d_recv, &mg->recv_cap, recv_total)) return B200SPH_ERR_CUDA;
+    {
+        size_t roff = 0;
+        for (int g = 0; g < n_groups; g++) {
+            if (n_out > 0)
+                MRC(b200sph_halo_pack_by_rank(h, fields + g_first[g], g_count[g], mg->d_order, mg->d_send_counts, W, n_out, mg->d_send));
+            if (mg_exchange_rows(mg, mg->d_send, mg->d_recv + roff, sc, rc, g_width[g])) return B200SPH_ERR_CUDA;
+            roff += (size_t)n_in * g_width[g];
+        }
+    }
     /* compact the stayers (their ascending indices are the tail of the sorted order), member by member through the
      * neighbour-list storage (void after a migration anyway), then append the arrivals */
     if (n_out > 0 && n_stay > 0) {
@@ -525,7 +544,13 @@ extern "C" int b200sph_mg_migrate(b200sph_mg *mg, const b200sph_view *view, cons
             }
         }
     }
-    if (n_in > 0) MRC(b200sph_halo_unpack_by_rank(h, fields, nf, mg->d_recv, mg->d_recv_counts, W, n_in, n_stay));
+    if (n_in > 0) {
+        size_t roff = 0;
+        for (int g = 0; g < n_groups; g++) {
+            MRC(b200sph_halo_unpack_by_rank(h, fields + g_first[g], g_count[g], mg->d_recv + roff, mg->d_recv_counts, W, n_in, n_stay));
+            roff += (size_t)n_in * g_width[g];
+        }
+    }
     MCU(cudaStreamSynchronize(st));
     MCU(cudaGetLastError());
     *n_held_out = n_stay + n_in;
