@@ -337,7 +337,7 @@ def main() -> None:
     ap.add_argument("--particles", type=int, default=None, help="particles per GPU (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--mg-host", default="python", choices=["python", "native"],
+    ap.add_argument("--mg-host", default="native", choices=["python", "native"],
                     help="several GPUs: host layer of the exchange -- miluphcuda_b200/multigpu.py over torch.distributed, or the C++/NCCL "
                          "host behind the C-ABI (csrc/mg.cu, b200sph_mg_*)")
     ap.add_argument("--halo-headroom", type=float, default=1.6, help="capacity of a rank's buffers over its owned particles")
