@@ -13,7 +13,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+# B200SPH_LIBDIR: measurement sessions build compile-time variants into their own directory and pick them per run
+LIBDIR = os.environ.get("B200SPH_LIBDIR") or os.path.join(HERE, "lib")
 CONFIGS = ("shocktube", "sedov", "rings", "impact", "giant_hydro", "giant_solid", "nakamura")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CU_SOURCES = ("libb200sph.cu",)

@@ -140,6 +140,8 @@ extern "C" int b200sph_create(b200sph_handle **out, int n_max, int device, uint6
         const char *env = getenv("B200SPH_FORCES_THREADS");
         const int t = env ? atoi(env) : 0;
         if (t == 32 || t == 64 || t == 96 || t == 128) h->forces_threads = t;
+        const char *ov = getenv("B200SPH_OVERLAP_POINTWISE");   /* measurement switch; the default is what ships */
+        h->overlap_pointwise = ov ? atoi(ov) : 1;
         const char *pad = getenv("B200SPH_PAD_SMEM");
         h->pad_smem = pad ? atoi(pad) : 0;
         if (h->pad_smem < 0 || h->pad_smem > 48 * 1024) h->pad_smem = 0;
@@ -160,6 +162,11 @@ extern "C" int b200sph_destroy(b200sph_handle *h)
     cudaFree(h->keys_in); cudaFree(h->idx_in); cudaFree(h->rho_sorted); cudaFree(h->block_partials);
     cudaFree(h->block_counter); cudaFree(h->d_flags); cudaFree(h->d_domain); cudaFree(h->cub_tmp);
     cudaFree(h->stage);
+    if (h->aux_stream) {
+        cudaStreamDestroy(h->aux_stream);
+        cudaEventDestroy(h->ev_fork);
+        cudaEventDestroy(h->ev_join);
+    }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int k = 0; k < 4; k++)
         if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]);

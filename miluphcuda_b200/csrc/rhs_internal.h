@@ -155,6 +155,9 @@ struct b200sph_handle {
     int halo_sums_external;     /* b200sph_set_halo_sums */
     const int *abort_flag;      /* b200sph_set_abort_flag */
     int lists_validated, stage_launches;   /* carried between the stages of one evaluation */
+    int overlap_pointwise, pointwise_early;   /* k_pointwise beside k_neighbours on aux_stream */
+    cudaStream_t aux_stream;
+    cudaEvent_t ev_fork, ev_join;
     const double *grav_src[4];  /* x, y, z, m of the global particle set (multi-GPU gravity), device pointers */
     int grav_src_n, grav_own_begin;
     int pad_smem;               /* profiling knob (B200SPH_PAD_SMEM): dynamic shared memory per pair-loop block, throttles occupancy */
