@@ -383,6 +383,12 @@ int b200sph_mg_decompose(b200sph_mg *mg, const b200sph_view *view, int n_held, i
 int b200sph_mg_migrate(b200sph_mg *mg, const b200sph_view *view, const b200sph_particle_arrays *extra, int n_extra, int n_held,
                        int capacity, int *n_held_out);
 int b200sph_mg_rhs_eval(b200sph_mg *mg, const b200sph_view *view, int n_owned, int capacity, int *n_total_out, int *offender);
+/* rk2_adaptive over the GPUs of one box: b200sph_rk2_advance with the evaluation going through b200sph_mg_rhs_eval and
+ * the step-size reductions (limitTimestepCourant/Damage: min; checkError: max, src/rk2adaptive.cu:521-695,1134-1482)
+ * all-reduced over the ranks, so that every rank takes the same steps.  Call b200sph_rk2_init for the owned rows first. */
+int b200sph_mg_rk2_advance(b200sph_mg *mg, const b200sph_view *view, const b200sph_particle_arrays rk[3],
+                           const b200sph_rk2_params *prm, double t_end, b200sph_rk2_state *state, int n_owned, int capacity,
+                           int *offender);
 int b200sph_mg_get_stats(const b200sph_mg *mg, b200sph_mg_stats *out);
 
 #ifdef __cplusplus

@@ -162,6 +162,8 @@ _EXPORTS = {
     "b200sph_mg_decompose": (C.c_int, [C.c_void_p, C.POINTER(View), C.c_int, C.c_int]),
     "b200sph_mg_migrate": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(ParticleArrays), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "b200sph_mg_rhs_eval": (C.c_int, [C.c_void_p, C.POINTER(View), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200sph_mg_rk2_advance": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(ParticleArrays), C.POINTER(Rk2Params), C.c_double,
+                                         C.POINTER(Rk2State), C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "b200sph_mg_get_stats": (C.c_int, [C.c_void_p, C.POINTER(MgStats)]),
     "b200sph_conserved_quantities": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(Conserved)]),
     "b200sph_reorder": (C.c_int, [C.c_void_p, C.POINTER(View), C.POINTER(ParticleArrays), C.c_int, C.c_void_p]),
@@ -564,6 +566,11 @@ class NativeMultiGpu:
         n_total, off = C.c_int(0), C.c_int(-1)
         self._check(self.lib.b200sph_mg_rhs_eval(self.handle, C.byref(view), n_owned, capacity, C.byref(n_total), C.byref(off)), off.value)
         return n_total.value
+
+    def rk2_advance(self, view: View, rk, prm: "Rk2Params", t_end: float, state: "Rk2State", n_owned: int, capacity: int) -> None:
+        off = C.c_int(-1)
+        self._check(self.lib.b200sph_mg_rk2_advance(self.handle, C.byref(view), rk, C.byref(prm), t_end, C.byref(state), n_owned, capacity,
+                                                    C.byref(off)), off.value)
 
     def stats(self) -> dict:
         st = MgStats()

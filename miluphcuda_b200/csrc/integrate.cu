@@ -212,8 +212,8 @@ __global__ void k_rk_copy_vars(b200sph_particle_arrays dst, b200sph_particle_arr
  * evaluated in (rk[FIRST]), fused with "remember values of first step" (rk[START] <- rk[FIRST], variables and
  * derivatives, src/rk2adaptive.cu:262-271) */
 __global__ void __launch_bounds__(RK_THREADS)
-k_rk_limit_remember(RkBuffers b, int n, int use_courant, int use_forces, int use_damage, double courant_fact, double forces_fact,
-                    double max_damage_change, RkScalars *sc, double *partials, unsigned int *counter)
+k_rk_limit_remember(RkBuffers b, int n, int use_courant, int use_forces, int use_damage, double max_damage_change, RkScalars *sc,
+                    double *partials, unsigned int *counter)
 {
     double v[3] = {1e100, 1e100, 1e100};
     const b200sph_particle_arrays &q = b.first;
@@ -241,14 +241,19 @@ k_rk_limit_remember(RkBuffers b, int n, int use_courant, int use_forces, int use
     }
     double out[3];
     if (!rk_reduce<3>(v, true, partials, counter, out)) return;
-    double dt = sc->dt;
-    out[0] *= courant_fact;
-    out[1] *= forces_fact;
-    if (use_courant && out[0] < dt && out[0] > 0.0) dt = out[0];
-    if (use_forces && out[1] < dt && out[1] > 0.0) dt = out[1];
-    if (use_damage && out[2] < dt && out[2] > 0.0) dt = out[2];
-    sc->dt = dt;
+    /* this rank's minima; several GPUs all-reduce them (min) before k_rk_apply_limits */
     sc->limit[0] = out[0]; sc->limit[1] = out[1]; sc->limit[2] = out[2];
+}
+
+__global__ void k_rk_apply_limits(RkScalars *sc, int use_courant, int use_forces, int use_damage, double courant_fact, double forces_fact)
+{
+    double dt = sc->dt;
+    const double c = sc->limit[0] * courant_fact, f = sc->limit[1] * forces_fact, d = sc->limit[2];
+    if (use_courant && c < dt && c > 0.0) dt = c;
+    if (use_forces && f < dt && f > 0.0) dt = f;
+    if (use_damage && d < dt && d > 0.0) dt = d;
+    sc->dt = dt;
+    sc->limit[0] = c; sc->limit[1] = f;
 }
 
 /* integrateFirstStep, src/rk2adaptive.cu:700-842: rk[FIRST] = rk[START] + dt B21 k1 */
@@ -498,6 +503,16 @@ k_rk_third_check(RkBuffers b, const int *materialId, int n, b200sph_rk2_params p
     }
     double out[6];
     if (!rk_reduce<6>(e, false, partials, counter, out)) return;
+    /* this rank's maxima; several GPUs all-reduce them (max) before k_rk_finish_check */
+#pragma unroll
+    for (int k = 0; k < 6; k++) sc->err[k] = out[k];
+}
+
+__global__ void k_rk_finish_check(RkScalars *sc, b200sph_rk2_params prm)
+{
+    const double dt = sc->dt;
+    double out[6];
+    for (int k = 0; k < 6; k++) out[k] = sc->err[k];
     double tmp = out[0];
     if (prm.use_velocity_error) tmp = fmax(tmp, out[1]);
     if (prm.use_density_error) tmp = fmax(tmp, out[2]);
@@ -518,8 +533,6 @@ k_rk_third_check(RkBuffers b, const int *materialId, int n, b200sph_rk2_params p
         if (dt_new < dt) dt_new = dt;
     }
     sc->dt_new = dt_new;
-#pragma unroll
-    for (int k = 0; k < 6; k++) sc->err[k] = out[k];
 }
 
 /* a rejected step: rk[FIRST] <- rk[START], variables and derivatives (src/rk2adaptive.cu:477-484) */
@@ -581,6 +594,13 @@ static int rk_scratch(b200sph_handle *h)
     return 0;
 }
 
+/* the right-hand side the integrator evaluates: b200sph_rhs_eval, or the multi-GPU host's exchange + evaluation (mg.cu) */
+static int rk_rhs(b200sph_handle *h, const b200sph_view *bound, int *offender)
+{
+    if (h->rk_rhs_hook) return h->rk_rhs_hook(h->rk_hook_ctx, bound, offender);
+    return b200sph_rhs_eval(h, bound, offender);
+}
+
 static bool rk_buffers_ok(const b200sph_particle_arrays &a)
 {
     return a.x && a.vx && a.ax && a.dxdt && a.m && a.h && a.rho && a.drhodt && a.p && a.cs && a.noi;
@@ -631,11 +651,13 @@ extern "C" int b200sph_rk2_step(b200sph_handle *h, const b200sph_view *view, con
     double dt_host = state->dt;
     RCU(cudaMemcpyAsync(&sc->dt, &dt_host, sizeof(double), cudaMemcpyHostToDevice, st));
     k_rk_copy_vars<<<G, RK_THREADS, 0, st>>>(rk[1], view->p, n);
-    if ((rc = b200sph_rhs_eval(h, &v1, offender)) != 0) return rc;
+    if ((rc = rk_rhs(h, &v1, offender)) != 0) return rc;
     state->rhs_calls++;
     k_rk_limit_remember<<<GR, RK_THREADS, 0, st>>>(b, n, prm->use_courant_limit, prm->use_forces_limit, prm->use_damage_limit,
-                                                 prm->courant_fact, prm->forces_fact, prm->max_damage_change, sc, h->rk_partials,
-                                                 h->rk_counter);
+                                                 prm->max_damage_change, sc, h->rk_partials, h->rk_counter);
+    if (h->rk_allreduce && (rc = h->rk_allreduce(h->rk_hook_ctx, sc->limit, 3, 1)) != 0) return rc;
+    k_rk_apply_limits<<<1, 1, 0, st>>>(sc, prm->use_courant_limit, prm->use_forces_limit, prm->use_damage_limit, prm->courant_fact,
+                                       prm->forces_fact);
     for (;;) {
         k_rk_first<<<G, RK_THREADS, 0, st>>>(b, n, sc);
         RCU(cudaMemcpyAsync(&hs, sc, sizeof(RkScalars), cudaMemcpyDeviceToHost, st));
@@ -645,11 +667,13 @@ extern "C" int b200sph_rk2_step(b200sph_handle *h, const b200sph_view *view, con
             snprintf(h->err, sizeof(h->err), "timestep %e is below SMALLEST_DT_ALLOWED (src/rk2adaptive.cu:281-284)", dt_host);
             return B200SPH_ERR_BAD_ARGUMENT;
         }
-        if ((rc = b200sph_rhs_eval(h, &v1, offender)) != 0) return rc;
+        if ((rc = rk_rhs(h, &v1, offender)) != 0) return rc;
         k_rk_second<<<G, RK_THREADS, 0, st>>>(b, n, sc, view->selfgravity);
-        if ((rc = b200sph_rhs_eval(h, &v2, offender)) != 0) return rc;
+        if ((rc = rk_rhs(h, &v2, offender)) != 0) return rc;
         state->rhs_calls += 2;
         k_rk_third_check<<<GR, RK_THREADS, 0, st>>>(b, view->p_rhs.materialId, n, *prm, sc, h->rk_partials, h->rk_counter);
+        if (h->rk_allreduce && (rc = h->rk_allreduce(h->rk_hook_ctx, sc->err, 6, 0)) != 0) return rc;
+        k_rk_finish_check<<<1, 1, 0, st>>>(sc, *prm);
         RCU(cudaMemcpyAsync(&hs, sc, sizeof(RkScalars), cudaMemcpyDeviceToHost, st));
         RCU(cudaStreamSynchronize(st));
         RCU(cudaGetLastError());

@@ -740,6 +740,52 @@ extern "C" int b200sph_mg_rhs_eval(b200sph_mg *mg, const b200sph_view *view, int
     return B200SPH_ERR_ABORTED;
 }
 
+/* ------------------------------------------------------------------ rk2_adaptive over several GPUs
+ * b200sph_rk2_step / b200sph_rk2_advance (integrate.cu) with the right-hand side going through b200sph_mg_rhs_eval and
+ * the step-size reductions all-reduced over the ranks ("global reductions moved out of single-GPU kernels":
+ * limitTimestepCourant/Damage -> min, checkError -> max).  Every rank takes the same steps.  All arrays of `view` and of
+ * the rk buffers have room for `capacity` rows; view->n is ignored in favour of n_owned. */
+struct MgRkCtx {
+    b200sph_mg *mg;
+    int n_owned, capacity;
+};
+
+static int mg_rk_rhs(void *ctx, const b200sph_view *bound, int *offender)
+{
+    MgRkCtx *c = (MgRkCtx *)ctx;
+    return b200sph_mg_rhs_eval(c->mg, bound, c->n_owned, c->capacity, nullptr, offender);
+}
+
+static int mg_rk_allreduce(void *ctx, double *dev_values, int n, int is_min)
+{
+    b200sph_mg *mg = ((MgRkCtx *)ctx)->mg;
+    MNC(g_nccl.AllReduce(dev_values, dev_values, n, ncclDouble, is_min ? ncclMin : ncclMax, mg->comm, mg->h->stream));
+    return 0;
+}
+
+extern "C" int b200sph_mg_rk2_advance(b200sph_mg *mg, const b200sph_view *view, const b200sph_particle_arrays rk[3],
+                                      const b200sph_rk2_params *prm, double t_end, b200sph_rk2_state *state, int n_owned, int capacity,
+                                      int *offender)
+{
+    if (!mg || !view || !rk || !prm || !state || n_owned <= 0 || capacity < n_owned) return B200SPH_ERR_BAD_ARGUMENT;
+    b200sph_handle *h = mg->h;
+    MgRkCtx ctx = {mg, n_owned, capacity};
+    b200sph_view v = *view;
+    v.n = n_owned;
+    v.n_real = n_owned;
+    h->rk_rhs_hook = mg_rk_rhs;
+    h->rk_allreduce = (mg->world > 1) ? mg_rk_allreduce : nullptr;
+    h->rk_hook_ctx = &ctx;
+    /* the cold calls of the output path (damageLimit) see owned rows only */
+    MRC(b200sph_set_owned(h, 0));
+    const int rc = b200sph_rk2_advance(h, &v, rk, prm, t_end, state, offender);
+    h->rk_rhs_hook = nullptr;
+    h->rk_allreduce = nullptr;
+    h->rk_hook_ctx = nullptr;
+    if (rc && !mg->err[0]) snprintf(mg->err, sizeof(mg->err), "%s", b200sph_last_error(h));
+    return rc;
+}
+
 extern "C" int b200sph_mg_get_stats(const b200sph_mg *mg, b200sph_mg_stats *out)
 {
     if (!mg || !out) return B200SPH_ERR_BAD_ARGUMENT;

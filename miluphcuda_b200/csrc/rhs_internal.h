@@ -178,6 +178,11 @@ struct b200sph_handle {
     cudaEvent_t hook_wait_before_pointwise;
     void (*hook_after_pointwise)(struct b200sph_handle *, void *);
     void *hook_ctx;
+    /* integrate.cu on several GPUs (set by mg.cu): the evaluation goes through the halo exchange, and the step-size
+     * reductions (device doubles) are all-reduced over the ranks, min or max */
+    int (*rk_rhs_hook)(void *ctx, const b200sph_view *bound, int *offender);
+    int (*rk_allreduce)(void *ctx, double *dev_values, int n, int is_min);
+    void *rk_hook_ctx;
     void *rk_scalars;           /* integrate.cu: device step state, reduction partials, ticket */
     double *rk_partials;
     unsigned int *rk_counter;
