@@ -582,12 +582,15 @@ def main() -> None:
     gbs = bytes_alg / (ms_forces * 1e-3) / 1e9 if ms_forces > 0 else 0.0
     # DRAM bytes of one k_forces launch from the committed `ncu --set full` capture of this workload (None if none exists)
     traffic = None
-    tpath = os.path.join(REPO, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as fh:
-            traffic = (json.load(fh).get(workload) or {}).get("k_forces_dram_bytes_per_launch")
+    traffic_source = None
+    for tname in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):  # newest capture that holds this workload
+        tpath = os.path.join(REPO, "profiles", tname)
+        if traffic is None and os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = (json.load(fh).get(workload) or {}).get("k_forces_dram_bytes_per_launch")
+            traffic_source = "profiles/" + tname if traffic is not None else None
     roof = {"bound": "fp64", "kernel": "k_forces", "achieved": tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
-            "frac": tf / peaks["fp64_tflops"], "traffic": traffic, "peak_source": peaks["fp64_source"],
+            "frac": tf / peaks["fp64_tflops"], "traffic": traffic, "traffic_source": traffic_source, "peak_source": peaks["fp64_source"],
             "ms_per_launch": ms_forces, "pairs_per_launch": pairs, "flop_per_pair": kind["force_flop_per_pair"],
             "hbm": {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                     "peak_source": peaks["hbm_source"], "bytes_per_particle": kind["force_bytes_per_particle"]},
