@@ -670,6 +670,112 @@ __device__ __forceinline__ void load_force_recs(const Sorted &s, int j, PairRecs
     r.g = ld_rec(&s.gas4[j]);
 }
 
+/* ------------------------------------------------------------------ teams of lanes
+ * The pair loops are bound by L1TEX wavefronts -- one per distinct 128-byte line a warp-wide record load touches
+ * (rhs_internal.h).  With one particle per lane the 32 lanes of a warp walk 32 different lists and touch ~0.68 lines
+ * per pair; with a team of 4 lanes on consecutive entries of ONE list (ascending cell order: runs of neighbours share
+ * lines) and 8 adjacent particles per warp it is ~0.40, and the trip count of a warp follows the longest list / 4 of
+ * 8 particles instead of the longest of 32 (numbers: impact lattice, tools/sim_lines.py).  The partial sums of a team
+ * meet in a shuffle butterfly, so a particle's sum is added in a different order than with one lane (rounding-level). */
+#ifndef B200_FORCES_TEAM
+#define B200_FORCES_TEAM 4
+#endif
+#define FORCES_TEAM_THREADS 128
+constexpr int kTeam = B200_FORCES_TEAM, kTeamParticles = FORCES_TEAM_THREADS / kTeam;
+static_assert(kTeam >= 2 && kTeam <= 32 && (kTeam & (kTeam - 1)) == 0, "team size: a power of two within a warp");
+constexpr unsigned int kTeamBits = (kTeam == 32) ? 0xffffffffu : ((1u << (kTeam & 31)) - 1u);
+#if SOLID
+constexpr int kForceSums = 7 + DIM * DIM;
+#else
+constexpr int kForceSums = 7;
+#endif
+
+__device__ __forceinline__ double team_sum(double x, unsigned int mask)
+{
+#pragma unroll
+    for (int o = kTeam / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o);
+    return x;
+}
+__device__ __forceinline__ double team_max(double x, unsigned int mask)
+{
+#pragma unroll
+    for (int o = kTeam / 2; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(mask, x, o));
+    return x;
+}
+/* LIST_VALIDATE with a team: the lanes hold kTeam consecutive entries; the kept ones move up to slot cnt, cnt + 1, ...
+ * (never past the slot they came from, and every later read of the team is at least 2 kTeam slots further on) */
+__device__ __forceinline__ void team_compact(const Sorted &s, int t, int q, int j, bool keep, int sub, unsigned int team_mask, int &cnt)
+{
+    const unsigned int b = (__ballot_sync(team_mask, keep) >> ((threadIdx.x & 31) & ~(kTeam - 1))) & kTeamBits;
+    const int pos = cnt + __popc(b & ((1u << sub) - 1u));
+    if (keep && pos != q) s.nbr[NBR_SLOT(t, pos)] = j;
+    cnt += __popc(b);
+}
+
+#if !INTEGRATE_DENSITY
+/* k_density<LIST_VALIDATE> with a team of lanes per particle */
+__global__ void __launch_bounds__(FORCES_TEAM_THREADS)
+k_density_team(Sorted s, b200sph_view v, double *rho_sorted, int n_targets, int *flags)
+{
+    const int sub = threadIdx.x % kTeam;
+    const int t = blockIdx.x * kTeamParticles + threadIdx.x / kTeam, k = t;
+    const unsigned int team_mask = kTeamBits << ((threadIdx.x & 31) & ~(kTeam - 1));
+    if (t >= n_targets) return;   /* whole teams leave together */
+    const int matId = s.mat[k];
+    const int i = s.perm[k];
+    const Rec4 pi = ld_rec(&s.pos4[k]);
+    const int nslots = s.noi[t];
+    if (s.abort && *s.abort) return;
+    if (s.halo_sums_external && i >= s.n_owned) return;   /* the owner sends this copy's density (b200sph_rhs_eval_stage) */
+    const bool summed = !mat_ignored(matId);
+    const double hinv_i = 1.0 / pi.w;
+    const double h2_i = __dmul_rn(pi.w, pi.w);
+    double rho = 0.0;
+    int cnt = 0;
+    if (nslots > 0) {
+        const int last = nslots - 1;
+        int j_next = s.nbr[NBR_SLOT(t, min(sub, last))];
+        int j_next2 = s.nbr[NBR_SLOT(t, min(sub + kTeam, last))];
+        Rec4 pj_next = ld_rec(&s.pos4[j_next]);
+        double mj_next = s.vel4[j_next].w;
+        for (int q0 = 0; q0 < nslots; q0 += kTeam) {
+            const int q = q0 + sub;
+            const int j = j_next;
+            const Rec4 pj = pj_next;
+            const double mj = mj_next;
+            j_next = j_next2;
+            j_next2 = s.nbr[NBR_SLOT(t, min(q + 2 * kTeam, last))];
+            pj_next = ld_rec(&s.pos4[j_next]);
+            mj_next = s.vel4[j_next].w;
+            double dx, dy, dz, W, g;
+            const double r2 = pair_d2(pi, pj, dx, dy, dz);
+            const bool keep = q < nslots && j != k && pair_is_neighbour(r2, h2_i, pj);
+            team_compact(s, t, q, j, keep, sub, team_mask, cnt);
+            if (!keep || !summed || (s.any_eos_ignore && mat_ignored(s.mat[j]))) continue;
+#if AVERAGE_KERNELS
+            cubic_spline(r2, hinv_i, W, g);   /* see k_density */
+            if (pj.w != pi.w) {
+                double Wj;
+                cubic_spline(r2, 1.0 / pj.w, Wj, g);
+                W = 0.5 * (W + Wj);
+            }
+#elif VARIABLE_SML || INTEGRATE_SML
+            cubic_spline(r2, 1.0 / (0.5 * (pi.w + pj.w)), W, g);
+#else
+            cubic_spline(r2, hinv_i, W, g);
+#endif
+            rho = fma(mj, W, rho);
+        }
+        rho = team_sum(rho, team_mask);
+    }
+    if (sub != 0) return;
+    finish_validate(s, t, k, cnt, flags);
+    rho += ld_rec(&s.vel4[k]).w * cubic_spline_w(0.0, hinv_i);
+    rho_sorted[k] = rho;
+    v.p.rho[i] = rho;
+}
+#endif
+
 /* ------------------------------------------------------------------ k_density */
 template <int MODE>
 __global__ void __launch_bounds__(128)
@@ -1242,6 +1348,139 @@ PAIR_UNROLL
 #endif
 
 #if TENSORIAL_CORRECTION
+/* k_correction with a team of lanes per particle; the matrix inversion runs one particle per lane again (first
+ * kTeamParticles threads of the block, sums handed over in shared memory) */
+template <int MODE>
+__global__ void __launch_bounds__(FORCES_TEAM_THREADS)
+k_correction_team(Sorted s, b200sph_view v, int n_targets, int *flags)
+{
+    __shared__ double sh_A[DIM * (DIM + 1) / 2][kTeamParticles];
+    {
+        const int sub = threadIdx.x % kTeam, slot = threadIdx.x / kTeam;
+        const int t = blockIdx.x * kTeamParticles + slot, k = t;
+        const unsigned int team_mask = kTeamBits << ((threadIdx.x & 31) & ~(kTeam - 1));
+        if (t < n_targets) {
+            const int i = s.perm[k];
+            if (!(s.halo_sums_external && i >= s.n_owned)) {
+                const Rec4 pi = ld_rec(&s.pos4[k]);
+                const int nslots = s.noi[t];
+                const bool summed = !mat_ignored(s.mat[k]);
+                double A[DIM][DIM];
+#pragma unroll
+                for (int a = 0; a < DIM; a++)
+#pragma unroll
+                    for (int b = 0; b < DIM; b++) A[a][b] = 0.0;
+                int cnt = 0;
+                if (nslots > 0 && (summed || MODE == LIST_VALIDATE)) {
+                    const double hinv = 1.0 / pi.w;   /* h_i, not the pair mean (src/kernel.cu:637) */
+                    const double h2_i = __dmul_rn(pi.w, pi.w);
+                    (void)h2_i;
+                    const int last = nslots - 1;
+                    int j_next = s.nbr[NBR_SLOT(t, min(sub, last))];
+                    int j_next2 = s.nbr[NBR_SLOT(t, min(sub + kTeam, last))];
+                    Rec4 pj_next = ld_rec(&s.pos4[j_next]);
+                    double vol_next = s.gas4[j_next].w;
+                    for (int q0 = 0; q0 < nslots; q0 += kTeam) {
+                        const int q = q0 + sub;
+                        const int j = j_next;
+                        const Rec4 pj = pj_next;
+                        const double vol_j = vol_next;   /* m_j / rho_j */
+                        j_next = j_next2;
+                        j_next2 = s.nbr[NBR_SLOT(t, min(q + 2 * kTeam, last))];
+                        pj_next = ld_rec(&s.pos4[j_next]);
+                        vol_next = s.gas4[j_next].w;
+                        double dr[3], W, g;
+                        const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
+                        bool keep = q < nslots;
+                        if (MODE != LIST_EXACT) keep = keep && j != k && pair_is_neighbour(r2, h2_i, pj);
+                        if (MODE == LIST_VALIDATE) team_compact(s, t, q, j, keep, sub, team_mask, cnt);
+                        if (!keep || !summed || (s.any_eos_ignore && mat_ignored(s.mat[j]))) continue;
+#if AVERAGE_KERNELS
+                        cubic_spline(r2, hinv, W, g);
+                        if (pj.w != pi.w) {
+                            double Wj, gj;
+                            cubic_spline(r2, 1.0 / pj.w, Wj, gj);
+                            g = 0.5 * (g + gj);
+                        }
+#else
+                        cubic_spline(r2, hinv, W, g);
+#endif
+                        const double w = vol_j * g;   /* (m_j/rho_j) * dW/dr / r */
+#pragma unroll
+                        for (int a = 0; a < DIM; a++) {
+                            const double wa = -w * dr[a];
+#pragma unroll
+                            for (int b = a; b < DIM; b++) A[a][b] = fma(wa, dr[b], A[a][b]);
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < DIM; a++)
+#pragma unroll
+                        for (int b = a; b < DIM; b++) A[a][b] = team_sum(A[a][b], team_mask);
+                }
+                if (sub == 0) {
+                    if (MODE == LIST_VALIDATE) finish_validate(s, t, k, cnt, flags);
+                    int c = 0;
+#pragma unroll
+                    for (int a = 0; a < DIM; a++)
+#pragma unroll
+                        for (int b = a; b < DIM; b++) sh_A[c++][slot] = A[a][b];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x >= kTeamParticles) return;
+    const int t = blockIdx.x * kTeamParticles + threadIdx.x, k = t;
+    if (t >= n_targets) return;
+    const int i = s.perm[k];
+    if (s.halo_sums_external && i >= s.n_owned) return;   /* the owner sends this copy's matrix; k_import_correction stores it */
+    double C[DIM][DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) C[a][b] = (a == b) ? 1.0 : 0.0;
+    if (!mat_ignored(s.mat[k])) {
+        double A[DIM][DIM];
+        int c = 0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = a; b < DIM; b++) {
+                A[a][b] = sh_A[c++][threadIdx.x];
+                A[b][a] = A[a][b];
+            }
+        sym_pinv(A, C);
+#if DIM == 2
+        const double det = C[0][0] * C[1][1] - C[0][1] * C[1][0];
+#else
+        const double det = C[0][0] * (C[1][1] * C[2][2] - C[1][2] * C[2][1]) - C[0][1] * (C[1][0] * C[2][2] - C[1][2] * C[2][0]) +
+                           C[0][2] * (C[1][0] * C[2][1] - C[1][1] * C[2][0]);
+#endif
+        double max_entry = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) max_entry = fmax(max_entry, fabs(C[a][b]));
+        if (fabs(det) < 0.2 || fabs(det) > 5.0 || max_entry > 5.0) {
+#pragma unroll
+            for (int a = 0; a < DIM; a++)
+#pragma unroll
+                for (int b = 0; b < DIM; b++) C[a][b] = (a == b) ? 1.0 : 0.0;
+        }
+    }
+    double *ten = reinterpret_cast<double *>(s.ten + (size_t)k * TEN_RECS);
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+            if (a <= b) ten[ten_c(a, b)] = C[a][b];
+            v.p_rhs.tensorialCorrectionMatrix[(size_t)i * DD + a * DIM + b] = C[a][b];
+        }
+}
+#endif
+
+#if TENSORIAL_CORRECTION
 /* Multi-GPU, neighbour-sum exchange: the correction matrices of the halo copies arrived in the caller's rows
  * (tensorialCorrectionMatrix, row-major DIM x DIM); the force loop reads them from the packed sorted records. */
 __global__ void k_import_correction(Sorted s, b200sph_view v)
@@ -1354,40 +1593,9 @@ PAIR_UNROLL
 }
 
 /* ------------------------------------------------------------------ k_forces_team
- * The same pair loop with B200_FORCES_TEAM lanes per particle.  The force loop is bound by L1TEX wavefronts -- one per
- * distinct 128-byte line a warp-wide record load touches (rhs_internal.h).  With one particle per lane the 32 lanes of a
- * warp walk 32 different lists and touch ~0.68 lines per pair; with a team of 4 lanes on consecutive entries of ONE
- * list (ascending cell order: runs of neighbours share lines) and 8 adjacent particles per warp it is ~0.40, and the
- * trip count of a warp follows the longest list / 4 of 8 particles instead of the longest of 32.  The partial sums
- * of a team meet in a shuffle butterfly; the per-particle epilogue runs one particle per lane again (first
- * FORCES_TEAM_THREADS / TEAM threads of the block, sums handed over in shared memory), so it costs what it did.
- * Only for validated lists (LIST_EXACT); the sums of a particle are added in a different order than in k_forces
- * (rounding-level difference). */
-#ifndef B200_FORCES_TEAM
-#define B200_FORCES_TEAM 4
-#endif
-#define FORCES_TEAM_THREADS 128
-constexpr int kTeam = B200_FORCES_TEAM, kTeamParticles = FORCES_TEAM_THREADS / kTeam;
-static_assert(kTeam >= 2 && kTeam <= 32 && (kTeam & (kTeam - 1)) == 0, "team size: a power of two within a warp");
-#if SOLID
-constexpr int kForceSums = 7 + DIM * DIM;
-#else
-constexpr int kForceSums = 7;
-#endif
-
-__device__ __forceinline__ double team_sum(double x, unsigned int mask)
-{
-#pragma unroll
-    for (int o = kTeam / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o);
-    return x;
-}
-__device__ __forceinline__ double team_max(double x, unsigned int mask)
-{
-#pragma unroll
-    for (int o = kTeam / 2; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(mask, x, o));
-    return x;
-}
-
+ * The same pair loop with a team of lanes per particle (see "teams of lanes" above).  The per-particle epilogue runs
+ * one particle per lane again (first kTeamParticles threads of the block, sums handed over in shared memory), so
+ * it costs what it did.  Only for validated lists (LIST_EXACT). */
 #ifdef B200_TEAM_MIN_BLOCKS   /* A/B switch (register cap) */
 #define TEAM_BOUNDS __launch_bounds__(FORCES_TEAM_THREADS, B200_TEAM_MIN_BLOCKS)
 #else
@@ -1396,7 +1604,8 @@ __device__ __forceinline__ double team_max(double x, unsigned int mask)
 __global__ void TEAM_BOUNDS
 k_forces_team(Sorted s, b200sph_view v, int n_targets, int *flags)
 {
-    constexpr int MODE = LIST_EXACT;
+    constexpr int MODE = LIST_EXACT;   /* read by the included pair body */
+    (void)MODE;
     __shared__ double sh_sum[kForceSums][kTeamParticles];
     const b200sph_particle_arrays &p = v.p;
     const b200sph_particle_arrays &pr = v.p_rhs;
@@ -1687,7 +1896,8 @@ static int rhs_stage_search(b200sph_handle *h, const b200sph_view &v)
 #if INTEGRATE_DENSITY
         k_density<LIST_CHECK><<<blocks_for(n, T), T, h->pad_smem, st>>>(s, v, h->rho_sorted, n, h->d_flags);
 #else
-        k_density<LIST_VALIDATE><<<blocks_for(n, T), T, h->pad_smem, st>>>(s, v, h->rho_sorted, n, h->d_flags);
+        if (h->pair_teams & 1) k_density_team<<<blocks_for(n, kTeamParticles), FORCES_TEAM_THREADS, h->pad_smem, st>>>(s, v, h->rho_sorted, n, h->d_flags);
+        else k_density<LIST_VALIDATE><<<blocks_for(n, T), T, h->pad_smem, st>>>(s, v, h->rho_sorted, n, h->d_flags);
         h->lists_validated = 1;
 #endif
         launches++;
@@ -1715,7 +1925,10 @@ static int rhs_stage_pointwise(b200sph_handle *h, const b200sph_view &v)
     if (h->hook_after_pointwise) h->hook_after_pointwise(h, h->hook_ctx);
     CU(cudaEventRecord(h->ev[4], st));
 #if TENSORIAL_CORRECTION
-    if (h->lists_validated) k_correction<LIST_EXACT><<<blocks_for(n, T), T, 0, st>>>(s, v, n, h->d_flags);
+    if (h->pair_teams & 2) {
+        if (h->lists_validated) k_correction_team<LIST_EXACT><<<blocks_for(n, kTeamParticles), FORCES_TEAM_THREADS, 0, st>>>(s, v, n, h->d_flags);
+        else k_correction_team<LIST_VALIDATE><<<blocks_for(n, kTeamParticles), FORCES_TEAM_THREADS, 0, st>>>(s, v, n, h->d_flags);
+    } else if (h->lists_validated) k_correction<LIST_EXACT><<<blocks_for(n, T), T, 0, st>>>(s, v, n, h->d_flags);
     else k_correction<LIST_VALIDATE><<<blocks_for(n, T), T, 0, st>>>(s, v, n, h->d_flags);
     h->lists_validated = 1;
     h->stage_launches++;
@@ -1739,7 +1952,7 @@ static int rhs_stage_forces(b200sph_handle *h, const b200sph_view &v, int *offen
 #endif
     const int TF = h->forces_threads;
     const size_t forces_smem = (size_t)h->pad_smem + ((SOLID && B200_ITENSORS_SMEM) ? (size_t)TF * TEN_RECS * 4 * sizeof(double) : 0);
-    if (h->lists_validated && h->forces_team) {
+    if (h->lists_validated && (h->pair_teams & 4)) {
         const size_t team_smem = (size_t)h->pad_smem + ((SOLID && B200_ITENSORS_SMEM) ? (size_t)FORCES_TEAM_THREADS * TEN_RECS * 4 * sizeof(double) : 0);
         k_forces_team<<<blocks_for(n, kTeamParticles), FORCES_TEAM_THREADS, team_smem, st>>>(s, v, n, h->d_flags);
     } else if (h->lists_validated) k_forces<LIST_EXACT><<<blocks_for(n, TF), TF, forces_smem, st>>>(s, v, n, h->d_flags);
