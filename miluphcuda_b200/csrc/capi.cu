@@ -142,9 +142,6 @@ extern "C" int b200sph_create(b200sph_handle **out, int n_max, int device, uint6
         if (t == 32 || t == 64 || t == 96 || t == 128) h->forces_threads = t;
         const char *ov = getenv("B200SPH_OVERLAP_POINTWISE");   /* measurement switch; the default is what ships */
         h->overlap_pointwise = ov ? atoi(ov) : 1;
-        /* measurement switch, bit mask: 1 k_density_team, 2 k_correction_team, 4 k_forces_team; 0 = one particle per lane everywhere */
-        const char *team = getenv("B200SPH_PAIR_TEAMS");
-        h->pair_teams = team ? atoi(team) : 7;
         const char *pad = getenv("B200SPH_PAD_SMEM");
         h->pad_smem = pad ? atoi(pad) : 0;
         if (h->pad_smem < 0 || h->pad_smem > 48 * 1024) h->pad_smem = 0;

@@ -161,7 +161,6 @@ struct b200sph_handle {
     const double *grav_src[4];  /* x, y, z, m of the global particle set (multi-GPU gravity), device pointers */
     int grav_src_n, grav_own_begin;
     int pad_smem;               /* profiling knob (B200SPH_PAD_SMEM): dynamic shared memory per pair-loop block, throttles occupancy */
-    int pair_teams;             /* bit mask of the pair loops that run with a team of lanes per particle (1 density, 2 correction, 4 forces) */
     int forces_threads;         /* block size of k_forces: small blocks keep more warps resident at high register counts */
     int have_global_domain;
     double global_lo[3], global_hi[3];

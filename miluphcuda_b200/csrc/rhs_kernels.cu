@@ -670,112 +670,6 @@ __device__ __forceinline__ void load_force_recs(const Sorted &s, int j, PairRecs
     r.g = ld_rec(&s.gas4[j]);
 }
 
-/* ------------------------------------------------------------------ teams of lanes
- * The pair loops are bound by L1TEX wavefronts -- one per distinct 128-byte line a warp-wide record load touches
- * (rhs_internal.h).  With one particle per lane the 32 lanes of a warp walk 32 different lists and touch ~0.68 lines
- * per pair; with a team of 4 lanes on consecutive entries of ONE list (ascending cell order: runs of neighbours share
- * lines) and 8 adjacent particles per warp it is ~0.40, and the trip count of a warp follows the longest list / 4 of
- * 8 particles instead of the longest of 32 (numbers: impact lattice, tools/sim_lines.py).  The partial sums of a team
- * meet in a shuffle butterfly, so a particle's sum is added in a different order than with one lane (rounding-level). */
-#ifndef B200_FORCES_TEAM
-#define B200_FORCES_TEAM 4
-#endif
-#define FORCES_TEAM_THREADS 128
-constexpr int kTeam = B200_FORCES_TEAM, kTeamParticles = FORCES_TEAM_THREADS / kTeam;
-static_assert(kTeam >= 2 && kTeam <= 32 && (kTeam & (kTeam - 1)) == 0, "team size: a power of two within a warp");
-constexpr unsigned int kTeamBits = (kTeam == 32) ? 0xffffffffu : ((1u << (kTeam & 31)) - 1u);
-#if SOLID
-constexpr int kForceSums = 7 + DIM * DIM;
-#else
-constexpr int kForceSums = 7;
-#endif
-
-__device__ __forceinline__ double team_sum(double x, unsigned int mask)
-{
-#pragma unroll
-    for (int o = kTeam / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o);
-    return x;
-}
-__device__ __forceinline__ double team_max(double x, unsigned int mask)
-{
-#pragma unroll
-    for (int o = kTeam / 2; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(mask, x, o));
-    return x;
-}
-/* LIST_VALIDATE with a team: the lanes hold kTeam consecutive entries; the kept ones move up to slot cnt, cnt + 1, ...
- * (never past the slot they came from, and every later read of the team is at least 2 kTeam slots further on) */
-__device__ __forceinline__ void team_compact(const Sorted &s, int t, int q, int j, bool keep, int sub, unsigned int team_mask, int &cnt)
-{
-    const unsigned int b = (__ballot_sync(team_mask, keep) >> ((threadIdx.x & 31) & ~(kTeam - 1))) & kTeamBits;
-    const int pos = cnt + __popc(b & ((1u << sub) - 1u));
-    if (keep && pos != q) s.nbr[NBR_SLOT(t, pos)] = j;
-    cnt += __popc(b);
-}
-
-#if !INTEGRATE_DENSITY
-/* k_density<LIST_VALIDATE> with a team of lanes per particle */
-__global__ void __launch_bounds__(FORCES_TEAM_THREADS)
-k_density_team(Sorted s, b200sph_view v, double *rho_sorted, int n_targets, int *flags)
-{
-    const int sub = threadIdx.x % kTeam;
-    const int t = blockIdx.x * kTeamParticles + threadIdx.x / kTeam, k = t;
-    const unsigned int team_mask = kTeamBits << ((threadIdx.x & 31) & ~(kTeam - 1));
-    if (t >= n_targets) return;   /* whole teams leave together */
-    const int matId = s.mat[k];
-    const int i = s.perm[k];
-    const Rec4 pi = ld_rec(&s.pos4[k]);
-    const int nslots = s.noi[t];
-    if (s.abort && *s.abort) return;
-    if (s.halo_sums_external && i >= s.n_owned) return;   /* the owner sends this copy's density (b200sph_rhs_eval_stage) */
-    const bool summed = !mat_ignored(matId);
-    const double hinv_i = 1.0 / pi.w;
-    const double h2_i = __dmul_rn(pi.w, pi.w);
-    double rho = 0.0;
-    int cnt = 0;
-    if (nslots > 0) {
-        const int last = nslots - 1;
-        int j_next = s.nbr[NBR_SLOT(t, min(sub, last))];
-        int j_next2 = s.nbr[NBR_SLOT(t, min(sub + kTeam, last))];
-        Rec4 pj_next = ld_rec(&s.pos4[j_next]);
-        double mj_next = s.vel4[j_next].w;
-        for (int q0 = 0; q0 < nslots; q0 += kTeam) {
-            const int q = q0 + sub;
-            const int j = j_next;
-            const Rec4 pj = pj_next;
-            const double mj = mj_next;
-            j_next = j_next2;
-            j_next2 = s.nbr[NBR_SLOT(t, min(q + 2 * kTeam, last))];
-            pj_next = ld_rec(&s.pos4[j_next]);
-            mj_next = s.vel4[j_next].w;
-            double dx, dy, dz, W, g;
-            const double r2 = pair_d2(pi, pj, dx, dy, dz);
-            const bool keep = q < nslots && j != k && pair_is_neighbour(r2, h2_i, pj);
-            team_compact(s, t, q, j, keep, sub, team_mask, cnt);
-            if (!keep || !summed || (s.any_eos_ignore && mat_ignored(s.mat[j]))) continue;
-#if AVERAGE_KERNELS
-            cubic_spline(r2, hinv_i, W, g);   /* see k_density */
-            if (pj.w != pi.w) {
-                double Wj;
-                cubic_spline(r2, 1.0 / pj.w, Wj, g);
-                W = 0.5 * (W + Wj);
-            }
-#elif VARIABLE_SML || INTEGRATE_SML
-            cubic_spline(r2, 1.0 / (0.5 * (pi.w + pj.w)), W, g);
-#else
-            cubic_spline(r2, hinv_i, W, g);
-#endif
-            rho = fma(mj, W, rho);
-        }
-        rho = team_sum(rho, team_mask);
-    }
-    if (sub != 0) return;
-    finish_validate(s, t, k, cnt, flags);
-    rho += ld_rec(&s.vel4[k]).w * cubic_spline_w(0.0, hinv_i);
-    rho_sorted[k] = rho;
-    v.p.rho[i] = rho;
-}
-#endif
-
 /* ------------------------------------------------------------------ k_density */
 template <int MODE>
 __global__ void __launch_bounds__(128)
@@ -1348,139 +1242,6 @@ PAIR_UNROLL
 #endif
 
 #if TENSORIAL_CORRECTION
-/* k_correction with a team of lanes per particle; the matrix inversion runs one particle per lane again (first
- * kTeamParticles threads of the block, sums handed over in shared memory) */
-template <int MODE>
-__global__ void __launch_bounds__(FORCES_TEAM_THREADS)
-k_correction_team(Sorted s, b200sph_view v, int n_targets, int *flags)
-{
-    __shared__ double sh_A[DIM * (DIM + 1) / 2][kTeamParticles];
-    {
-        const int sub = threadIdx.x % kTeam, slot = threadIdx.x / kTeam;
-        const int t = blockIdx.x * kTeamParticles + slot, k = t;
-        const unsigned int team_mask = kTeamBits << ((threadIdx.x & 31) & ~(kTeam - 1));
-        if (t < n_targets) {
-            const int i = s.perm[k];
-            if (!(s.halo_sums_external && i >= s.n_owned)) {
-                const Rec4 pi = ld_rec(&s.pos4[k]);
-                const int nslots = s.noi[t];
-                const bool summed = !mat_ignored(s.mat[k]);
-                double A[DIM][DIM];
-#pragma unroll
-                for (int a = 0; a < DIM; a++)
-#pragma unroll
-                    for (int b = 0; b < DIM; b++) A[a][b] = 0.0;
-                int cnt = 0;
-                if (nslots > 0 && (summed || MODE == LIST_VALIDATE)) {
-                    const double hinv = 1.0 / pi.w;   /* h_i, not the pair mean (src/kernel.cu:637) */
-                    const double h2_i = __dmul_rn(pi.w, pi.w);
-                    (void)h2_i;
-                    const int last = nslots - 1;
-                    int j_next = s.nbr[NBR_SLOT(t, min(sub, last))];
-                    int j_next2 = s.nbr[NBR_SLOT(t, min(sub + kTeam, last))];
-                    Rec4 pj_next = ld_rec(&s.pos4[j_next]);
-                    double vol_next = s.gas4[j_next].w;
-                    for (int q0 = 0; q0 < nslots; q0 += kTeam) {
-                        const int q = q0 + sub;
-                        const int j = j_next;
-                        const Rec4 pj = pj_next;
-                        const double vol_j = vol_next;   /* m_j / rho_j */
-                        j_next = j_next2;
-                        j_next2 = s.nbr[NBR_SLOT(t, min(q + 2 * kTeam, last))];
-                        pj_next = ld_rec(&s.pos4[j_next]);
-                        vol_next = s.gas4[j_next].w;
-                        double dr[3], W, g;
-                        const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
-                        bool keep = q < nslots;
-                        if (MODE != LIST_EXACT) keep = keep && j != k && pair_is_neighbour(r2, h2_i, pj);
-                        if (MODE == LIST_VALIDATE) team_compact(s, t, q, j, keep, sub, team_mask, cnt);
-                        if (!keep || !summed || (s.any_eos_ignore && mat_ignored(s.mat[j]))) continue;
-#if AVERAGE_KERNELS
-                        cubic_spline(r2, hinv, W, g);
-                        if (pj.w != pi.w) {
-                            double Wj, gj;
-                            cubic_spline(r2, 1.0 / pj.w, Wj, gj);
-                            g = 0.5 * (g + gj);
-                        }
-#else
-                        cubic_spline(r2, hinv, W, g);
-#endif
-                        const double w = vol_j * g;   /* (m_j/rho_j) * dW/dr / r */
-#pragma unroll
-                        for (int a = 0; a < DIM; a++) {
-                            const double wa = -w * dr[a];
-#pragma unroll
-                            for (int b = a; b < DIM; b++) A[a][b] = fma(wa, dr[b], A[a][b]);
-                        }
-                    }
-#pragma unroll
-                    for (int a = 0; a < DIM; a++)
-#pragma unroll
-                        for (int b = a; b < DIM; b++) A[a][b] = team_sum(A[a][b], team_mask);
-                }
-                if (sub == 0) {
-                    if (MODE == LIST_VALIDATE) finish_validate(s, t, k, cnt, flags);
-                    int c = 0;
-#pragma unroll
-                    for (int a = 0; a < DIM; a++)
-#pragma unroll
-                        for (int b = a; b < DIM; b++) sh_A[c++][slot] = A[a][b];
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x >= kTeamParticles) return;
-    const int t = blockIdx.x * kTeamParticles + threadIdx.x, k = t;
-    if (t >= n_targets) return;
-    const int i = s.perm[k];
-    if (s.halo_sums_external && i >= s.n_owned) return;   /* the owner sends this copy's matrix; k_import_correction stores it */
-    double C[DIM][DIM];
-#pragma unroll
-    for (int a = 0; a < DIM; a++)
-#pragma unroll
-        for (int b = 0; b < DIM; b++) C[a][b] = (a == b) ? 1.0 : 0.0;
-    if (!mat_ignored(s.mat[k])) {
-        double A[DIM][DIM];
-        int c = 0;
-#pragma unroll
-        for (int a = 0; a < DIM; a++)
-#pragma unroll
-            for (int b = a; b < DIM; b++) {
-                A[a][b] = sh_A[c++][threadIdx.x];
-                A[b][a] = A[a][b];
-            }
-        sym_pinv(A, C);
-#if DIM == 2
-        const double det = C[0][0] * C[1][1] - C[0][1] * C[1][0];
-#else
-        const double det = C[0][0] * (C[1][1] * C[2][2] - C[1][2] * C[2][1]) - C[0][1] * (C[1][0] * C[2][2] - C[1][2] * C[2][0]) +
-                           C[0][2] * (C[1][0] * C[2][1] - C[1][1] * C[2][0]);
-#endif
-        double max_entry = 0.0;
-#pragma unroll
-        for (int a = 0; a < DIM; a++)
-#pragma unroll
-            for (int b = 0; b < DIM; b++) max_entry = fmax(max_entry, fabs(C[a][b]));
-        if (fabs(det) < 0.2 || fabs(det) > 5.0 || max_entry > 5.0) {
-#pragma unroll
-            for (int a = 0; a < DIM; a++)
-#pragma unroll
-                for (int b = 0; b < DIM; b++) C[a][b] = (a == b) ? 1.0 : 0.0;
-        }
-    }
-    double *ten = reinterpret_cast<double *>(s.ten + (size_t)k * TEN_RECS);
-#pragma unroll
-    for (int a = 0; a < DIM; a++)
-#pragma unroll
-        for (int b = 0; b < DIM; b++) {
-            if (a <= b) ten[ten_c(a, b)] = C[a][b];
-            v.p_rhs.tensorialCorrectionMatrix[(size_t)i * DD + a * DIM + b] = C[a][b];
-        }
-}
-#endif
-
-#if TENSORIAL_CORRECTION
 /* Multi-GPU, neighbour-sum exchange: the correction matrices of the halo copies arrived in the caller's rows
  * (tensorialCorrectionMatrix, row-major DIM x DIM); the force loop reads them from the packed sorted records. */
 __global__ void k_import_correction(Sorted s, b200sph_view v)
@@ -1558,10 +1319,82 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
     int noi = nslots;
 
     const bool active = !(matId == BOUNDARY_PARTICLE_ID || mat_ignored(matId)) && i < v.n_real;
-#include "forces_decl.inc"
+    double acc[3] = {0.0, 0.0, 0.0}, drhodt = 0.0, dedt = 0.0, dhdt = 0.0, muijmax = 0.0;
+    (void)dedt; (void)dhdt; (void)muijmax;
+#if SOLID
+    double vgrad[DIM][DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) vgrad[a][b] = 0.0;
+#if B200_ITENSORS_SMEM
+    /* the particle's own tensors (sigma/rho^2, C, R/rho^2: up to 18 doubles) live in shared memory, one column per
+     * thread (conflict-free), and are re-read per pair instead of pinning 24-36 registers for the whole loop */
+    extern __shared__ double sh_ti[];
+    double *const my_ti = sh_ti + threadIdx.x;
+    const int ti_stride = blockDim.x;
+#define TI(idx) lds_f64(my_ti + (idx) * ti_stride)
+#else
+    double sig_i[DIM][DIM];
+#if TENSORIAL_CORRECTION
+    double Ci[DIM][DIM];
+#endif
+#if ARTIFICIAL_STRESS
+    double Ri[DIM][DIM];
+#endif
+#endif
+#endif
 
     if (active && nslots > 0) {
-#include "forces_self.inc"
+        const MatParams &M = c_mat[matId];
+        const Rec4 gi = ld_rec(&s.gas4[k]);
+        const double h2_i = __dmul_rn(pi.w, pi.w);
+        int cnt = 0;
+        (void)h2_i; (void)cnt;
+        const double rho_i = gi.z;
+        (void)rho_i;
+#if ARTIFICIAL_VISCOSITY
+        const double av_alpha = M.av_alpha, av_beta = M.av_beta;
+#endif
+#if SOLID
+        {
+            double ti[4 * TEN_RECS];
+#pragma unroll
+            for (int r = 0; r < TEN_RECS; r++) {
+                const Rec4 t = ld_rec(&s.ten[(size_t)k * TEN_RECS + r]);
+                ti[4 * r] = t.x; ti[4 * r + 1] = t.y; ti[4 * r + 2] = t.z; ti[4 * r + 3] = t.w;
+            }
+#if B200_ITENSORS_SMEM
+#pragma unroll
+            for (int c = 0; c < TEN_DOUBLES; c++) my_ti[c * ti_stride] = ti[c];
+#else
+#pragma unroll
+            for (int a = 0; a < DIM; a++)
+#pragma unroll
+                for (int b = 0; b < DIM; b++) {
+                    sig_i[a][b] = ti[ten_sig(a, b)];
+#if TENSORIAL_CORRECTION
+                    Ci[a][b] = ti[ten_c(a, b)];
+#endif
+#if ARTIFICIAL_STRESS
+                    Ri[a][b] = ti[ten_r(a, b)];
+#endif
+                }
+#endif
+        }
+        const double m_over_rho_i_unit = 1.0 / rho_i;   /* strain rate uses m_j / rho_i (src/internal_forces.cu:476) */
+#endif
+#if !(VARIABLE_SML || INTEGRATE_SML)
+        const double hinv_fixed = 1.0 / pi.w;
+#endif
+#if ARTIFICIAL_STRESS
+        const double w_ref_dist = M.mean_particle_distance;
+        const double w_ref_same_h = cubic_spline_w(w_ref_dist, 1.0 / pi.w);
+        /* Monaghan's exponent is a small integer in every shipped material.cfg (n = 4): repeated multiplication
+         * instead of pow(); any other value takes the general path */
+        const int art_int_exp = (M.exponent_tensor >= 1.0 && M.exponent_tensor <= 8.0 && M.exponent_tensor == floor(M.exponent_tensor))
+                                    ? (int)M.exponent_tensor : 0;
+#endif
         int j_next = s.nbr[NBR_SLOT(t, 0)];
         int j_next2 = s.nbr[NBR_SLOT(t, min(1, nslots - 1))];
         PairRecs nxt;
@@ -1583,121 +1416,377 @@ PAIR_UNROLL
                 cnt++;
             }
             if (s.any_eos_ignore && mat_ignored(s.mat[j])) continue;
-#include "forces_pair.inc"
+            const Rec4 &vj = cur.v;
+            const Rec4 &gj = cur.g;
+#if SOLID
+            double tj[4 * TEN_RECS];
+#pragma unroll
+            for (int r = 0; r < TEN_RECS; r++) {
+                tj[4 * r] = cur.t[r].x; tj[4 * r + 1] = cur.t[r].y; tj[4 * r + 2] = cur.t[r].z; tj[4 * r + 3] = cur.t[r].w;
+            }
+#endif
+            dv[0] = vi.x - vj.x; dv[1] = vi.y - vj.y; dv[2] = vi.z - vj.z;
+#if VARIABLE_SML || INTEGRATE_SML
+            const double hbar = 0.5 * (pi.w + pj.w);
+            const double hinv = 1.0 / hbar;
+#else
+            /* fixed h; with AVERAGE_KERNELS and no SHEPARD_CORRECTION the reference also uses h_i
+             * only (the averaging lines are compiled out, src/internal_forces.cu:328-346) */
+            const double hinv = hinv_fixed;
+#endif
+            cubic_spline(r2, hinv, W, g);
+            double gw[DIM];   /* plain kernel gradient */
+#pragma unroll
+            for (int a = 0; a < DIM; a++) gw[a] = g * dr[a];
+            const double mj = vj.w;
+
+#if SOLID && B200_ITENSORS_SMEM
+            double sig_i[DIM][DIM];
+#if TENSORIAL_CORRECTION
+            double Ci[DIM][DIM];
+#endif
+#if ARTIFICIAL_STRESS
+            double Ri[DIM][DIM];
+#endif
+#pragma unroll
+            for (int a = 0; a < DIM; a++)
+#pragma unroll
+                for (int b = a; b < DIM; b++) {
+#if TEN_SIG_SYM
+                    sig_i[a][b] = sig_i[b][a] = TI(ten_sig(a, b));
+#else
+                    sig_i[a][b] = TI(ten_sig(a, b));
+                    if (a != b) sig_i[b][a] = TI(ten_sig(b, a));
+#endif
+#if TENSORIAL_CORRECTION
+                    Ci[a][b] = Ci[b][a] = TI(ten_c(a, b));
+#endif
+#if ARTIFICIAL_STRESS
+                    Ri[a][b] = Ri[b][a] = TI(ten_r(a, b));
+#endif
+                }
+#endif
+#if TENSORIAL_CORRECTION
+            double gci[DIM], gcj[DIM], gsym[DIM];
+#pragma unroll
+            for (int a = 0; a < DIM; a++) {
+                double tci = 0.0, tcj = 0.0;
+#pragma unroll
+                for (int b = 0; b < DIM; b++) {
+                    tci = fma(Ci[a][b], gw[b], tci);
+                    tcj = fma(tj[ten_c(a, b)], gw[b], tcj);
+                }
+                gci[a] = tci;
+                gcj[a] = tcj;
+                gsym[a] = 0.5 * (tci + tcj);
+            }
+#else
+            const double *gsym = gw;
+#endif
+            double vvnablaW = 0.0;
+#pragma unroll
+            for (int a = 0; a < DIM; a++) vvnablaW = fma(dv[a], gsym[a], vvnablaW);
+
+#if SOLID
+            /* strain rate and rotation rate, edot_ab = 1/2 (d_b v_a + d_a v_b) */
+            {
+                /* accumulate the velocity gradient L_ab = sum w dv_a grad_b; edot = L + L^T and
+                 * rdot = L - L^T are formed once after the loop (9 accumulators instead of 18) */
+                const double w = -0.5 * mj * m_over_rho_i_unit;
+#pragma unroll
+                for (int a = 0; a < DIM; a++) {
+                    const double wa = w * dv[a];
+#pragma unroll
+                    for (int b = 0; b < DIM; b++) vgrad[a][b] = fma(wa, gsym[b], vgrad[a][b]);
+                }
+            }
+#endif
+            double pij = 0.0;
+#if ARTIFICIAL_VISCOSITY
+            {
+                double vr = 0.0;
+#pragma unroll
+                for (int a = 0; a < DIM; a++) vr = fma(dv[a], dr[a], vr);
+                if (vr < 0.0) {
+                    const double csbar = 0.5 * (gi.y + gj.y);
+                    const double smooth = 0.5 * (pi.w + pj.w);
+                    /* mu = h vr / (r^2 + 0.01 h^2) and Pi = (beta mu - alpha c) mu / rho_bar with ONE division:
+                     * 1/(A B) gives 1/A = B/(A B) and 1/B = A/(A B) (rounding-level difference to two divisions) */
+                    const double den = fma(smooth * smooth, 1e-2, r2);
+                    const double rhobar = 0.5 * (gi.z + gj.z);
+                    const double inv = 1.0 / (den * rhobar);
+                    const double mu = smooth * vr * (inv * rhobar);
+                    muijmax = fmax(muijmax, mu);
+                    pij = (av_beta * mu - av_alpha * csbar) * mu * (inv * den);
+                }
+            }
+#endif
+#if SOLID
+            {
+                double aj[DIM];
+#pragma unroll
+                for (int a = 0; a < DIM; a++) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int b = 0; b < DIM; b++) {
+#if TENSORIAL_CORRECTION
+                        t = fma(tj[ten_sig(a, b)], gcj[b], t);
+                        t = fma(sig_i[a][b], gci[b], t);
+#else
+                        t = fma(tj[ten_sig(a, b)] + sig_i[a][b], gw[b], t);
+#endif
+                    }
+                    aj[a] = mj * t;
+                }
+#if ARTIFICIAL_STRESS
+                /* Monaghan (2000) tensile-instability fix: (W(r)/W(dp))^n * (R_i/rho_i^2 + R_j/rho_j^2) */
+                {
+                    const double hb = 0.5 * (pi.w + pj.w), hbinv = 1.0 / hb;
+                    const double r = sqrt(r2);
+                    /* W(mean particle distance) only depends on h_bar: hoisted for partners with h_j = h_i */
+                    const double w_ref = (pj.w == pi.w) ? w_ref_same_h : cubic_spline_w(w_ref_dist, hbinv);
+                    const double ratio = cubic_spline_w(r, hbinv) / w_ref;
+                    const double artf = (art_int_exp > 0) ? int_power(ratio, art_int_exp) : pow(ratio, M.exponent_tensor);
+#pragma unroll
+                    for (int a = 0; a < DIM; a++) {
+                        double t = 0.0;
+#pragma unroll
+                        for (int b = 0; b < DIM; b++) {
+#if TENSORIAL_CORRECTION
+                            t = fma(Ri[a][b], gci[b], t);
+                            t = fma(tj[ten_r(a, b)], gcj[b], t);
+#else
+                            t = fma(Ri[a][b] + tj[ten_r(a, b)], gw[b], t);
+#endif
+                        }
+                        const double art = mj * artf * t;
+                        acc[a] += art;
+#if INTEGRATE_ENERGY && TENSORIAL_CORRECTION
+                        dedt = fma(-0.5 * art, dv[a], dedt);
+#endif
+                    }
+                }
+#endif
+#pragma unroll
+                for (int a = 0; a < DIM; a++) acc[a] += aj[a];
+#if INTEGRATE_ENERGY
+                /* pairwise-conservative heating: 1/2 m_j (sigma_i/rho_i^2 grad_i + sigma_j/rho_j^2 grad_j) . dv */
+                {
+                    double t = 0.0;
+#pragma unroll
+                    for (int a = 0; a < DIM; a++) t = fma(aj[a], dv[a], t);
+                    dedt = fma(0.5, t, dedt);
+                }
+#endif
+            }
+#else /* HYDRO */
+            {
+                const double w = -mj * (gi.x + gj.x);
+                double t = 0.0;
+#pragma unroll
+                for (int a = 0; a < DIM; a++) {
+                    const double aj = w * gw[a];
+                    acc[a] += aj;
+                    t = fma(aj, dv[a], t);
+                }
+#if INTEGRATE_ENERGY
+                dedt = fma(-0.5, t, dedt);
+#endif
+            }
+#endif
+#if ARTIFICIAL_VISCOSITY
+            {
+                const double w = -mj * pij;
+#pragma unroll
+                for (int a = 0; a < DIM; a++) acc[a] = fma(w, gsym[a], acc[a]);
+#if INTEGRATE_ENERGY
+                if (!v.is_relaxation_run) dedt = fma(0.5 * mj * pij, vvnablaW, dedt);
+#endif
+            }
+#endif
+            drhodt = fma(gi.z * gj.w, vvnablaW, drhodt);            /* rho_i/rho_j m_j v.gradW */
+#if INTEGRATE_SML
+            dhdt = fma(-(1.0 / DIM) * pi.w * gj.w, vvnablaW, dhdt);
+#endif
         }
         if (MODE == LIST_VALIDATE) noi = finish_validate(s, t, k, cnt, flags);
     } else if (MODE == LIST_VALIDATE) {
         noi = finish_validate(s, t, k, validate_only(s, t, k, pi, nslots), flags);
     }
-#include "forces_epilogue.inc"
-}
+    p.noi[i] = noi;
 
-/* ------------------------------------------------------------------ k_forces_team
- * The same pair loop with a team of lanes per particle (see "teams of lanes" above).  The per-particle epilogue runs
- * one particle per lane again (first kTeamParticles threads of the block, sums handed over in shared memory), so
- * it costs what it did.  Only for validated lists (LIST_EXACT). */
-#ifdef B200_TEAM_MIN_BLOCKS   /* A/B switch (register cap) */
-#define TEAM_BOUNDS __launch_bounds__(FORCES_TEAM_THREADS, B200_TEAM_MIN_BLOCKS)
-#else
-#define TEAM_BOUNDS __launch_bounds__(FORCES_TEAM_THREADS)
+    /* ---------------- per-particle epilogue: everything the integrators read, in caller order */
+    if (!active) {
+        /* zero_all_derivatives + boundary hooks for deactivated / virtual particles */
+        p.ax[i] = 0.0; p.dxdt[i] = 0.0;
+#if DIM > 1
+        p.ay[i] = 0.0; p.dydt[i] = 0.0;
 #endif
-__global__ void TEAM_BOUNDS
-k_forces_team(Sorted s, b200sph_view v, int n_targets, int *flags)
-{
-    constexpr int MODE = LIST_EXACT;   /* read by the included pair body */
-    (void)MODE;
-    __shared__ double sh_sum[kForceSums][kTeamParticles];
-    const b200sph_particle_arrays &p = v.p;
-    const b200sph_particle_arrays &pr = v.p_rhs;
-    (void)pr; (void)flags;
-    const bool aborted = s.abort && *s.abort;
-    {
-        const int sub = threadIdx.x % kTeam, slot = threadIdx.x / kTeam;
-        const int t = blockIdx.x * kTeamParticles + slot, k = t;
-        const unsigned int team_mask = ((kTeam == 32) ? 0xffffffffu : ((1u << kTeam) - 1u)) << ((threadIdx.x & 31) & ~(kTeam - 1));
-        if (t < n_targets && !aborted) {
-            const int i = s.perm[k];
-            const int matId = s.mat[k];
-            if (i < s.n_owned) {
-                const Rec4 pi = ld_rec(&s.pos4[k]);
-                const Rec4 vi = ld_rec(&s.vel4[k]);
-                const int nslots = s.noi[t];
-                const bool active = !(matId == BOUNDARY_PARTICLE_ID || mat_ignored(matId)) && i < v.n_real;
-#include "forces_decl.inc"
-                if (active && nslots > 0) {
-#include "forces_self.inc"
-                    const int last = nslots - 1;
-                    int j_next = s.nbr[NBR_SLOT(t, min(sub, last))];
-                    int j_next2 = s.nbr[NBR_SLOT(t, min(sub + kTeam, last))];
-                    PairRecs nxt;
-                    load_force_recs(s, j_next, nxt);
-                    for (int q = sub; q < nslots; q += kTeam) {
-                        const int j = j_next;
-                        PairRecs cur = nxt;
-                        load_tensor_recs(s, j, cur);
-                        j_next = j_next2;
-                        j_next2 = s.nbr[NBR_SLOT(t, min(q + 2 * kTeam, last))];
-                        load_force_recs(s, j_next, nxt);   /* past the end this re-reads the last neighbour (harmless) */
-                        const Rec4 &pj = cur.p;
-                        double dr[3], dv[3], W, g;
-                        const double r2 = pair_d2(pi, pj, dr[0], dr[1], dr[2]);
-                        if (s.any_eos_ignore && mat_ignored(s.mat[j])) continue;
-#include "forces_pair.inc"
-                    }
-#pragma unroll
-                    for (int a = 0; a < 3; a++) acc[a] = team_sum(acc[a], team_mask);
-                    drhodt = team_sum(drhodt, team_mask);
+#if DIM > 2
+        p.az[i] = 0.0; p.dzdt[i] = 0.0;
+#endif
+        p.drhodt[i] = 0.0;
 #if INTEGRATE_ENERGY
-                    dedt = team_sum(dedt, team_mask);
+        p.dedt[i] = 0.0;
 #endif
 #if INTEGRATE_SML
-                    dhdt = team_sum(dhdt, team_mask);
-#endif
-#if ARTIFICIAL_VISCOSITY
-                    muijmax = team_max(muijmax, team_mask);
+        p.dhdt[i] = 0.0;
 #endif
 #if SOLID
 #pragma unroll
-                    for (int a = 0; a < DIM; a++)
-#pragma unroll
-                        for (int b = 0; b < DIM; b++) vgrad[a][b] = team_sum(vgrad[a][b], team_mask);
+        for (int a = 0; a < DD; a++) p.dSdt[(size_t)i * DD + a] = 0.0;
 #endif
-                }
-                if (sub == 0) {
-                    sh_sum[0][slot] = acc[0]; sh_sum[1][slot] = acc[1]; sh_sum[2][slot] = acc[2];
-                    sh_sum[3][slot] = drhodt; sh_sum[4][slot] = dedt; sh_sum[5][slot] = dhdt; sh_sum[6][slot] = muijmax;
-#if SOLID
-#pragma unroll
-                    for (int a = 0; a < DIM; a++)
-#pragma unroll
-                        for (int b = 0; b < DIM; b++) sh_sum[7 + a * DIM + b][slot] = vgrad[a][b];
+#if FRAGMENTATION
+        p.dddt[i] = 0.0;
 #endif
-                }
-            }
+        return;
+    }
+
+    const MatParams &M = c_mat[matId];
+    p.ax[i] = acc[0]; p.dxdt[i] = vi.x;
+#if DIM > 1
+    p.ay[i] = acc[1]; p.dydt[i] = vi.y;
+#endif
+#if DIM > 2
+    p.az[i] = acc[2]; p.dzdt[i] = vi.z;
+#endif
+#if INTEGRATE_DENSITY
+    if (M.density_via_kernel_sum) drhodt = 0.0;
+#endif
+    /* BoundaryConditionsAfterRHS floors (src/boundary.cu:311-324) act on the stored rate only */
+    if (s.gas4[k].z < M.density_floor) {
+        p.rho[i] = M.density_floor;
+        p.drhodt[i] = 0.0;
+    } else {
+        p.drhodt[i] = drhodt;
+    }
+#if INTEGRATE_ENERGY
+    p.dedt[i] = dedt;
+#endif
+#if INTEGRATE_SML
+    p.dhdt[i] = dhdt;
+#endif
+#if PALPHA_POROSITY
+    double dalphadt = 0.0, alpha_now = p.alpha_jutzi[i];
+    if (noi > 0 && (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN || M.eos == EOS_TYPE_JUTZI_ANEOS)) {
+        if (alpha_now <= 1.0) {
+            alpha_now = 1.0;
+            p.alpha_jutzi[i] = 1.0;
+        } else {
+            const double dadp = p.dalphadp[i], dpdr = p.delpdelrho[i];
+#if INTEGRATE_ENERGY
+            dalphadt = ((dedt * p.delpdele[i] + alpha_now * drhodt * dpdr) * dadp) / (alpha_now + dadp * (p.p[i] - s.gas4[k].z * dpdr));
+#else
+            dalphadt = ((alpha_now * drhodt * dpdr) * dadp) / (alpha_now + dadp * (p.p[i] - s.gas4[k].z * dpdr));
+#endif
+            if (dalphadt > 0.0) dalphadt = 0.0;
         }
     }
-    __syncthreads();
-    if (threadIdx.x >= kTeamParticles || aborted) return;
-    const int t = blockIdx.x * kTeamParticles + threadIdx.x, k = t;
-    if (t >= n_targets) return;
-    const int i = s.perm[k];
-    const int matId = s.mat[k];
-    if (i >= s.n_owned) return;   /* halo copy: its owner computes the rates */
-    const Rec4 pi = ld_rec(&s.pos4[k]);
-    const Rec4 vi = ld_rec(&s.vel4[k]);
-    const int noi = s.noi[t];
-    const bool active = !(matId == BOUNDARY_PARTICLE_ID || mat_ignored(matId)) && i < v.n_real;
-    double acc[3] = {sh_sum[0][threadIdx.x], sh_sum[1][threadIdx.x], sh_sum[2][threadIdx.x]};
-    double drhodt = sh_sum[3][threadIdx.x], dedt = sh_sum[4][threadIdx.x], dhdt = sh_sum[5][threadIdx.x], muijmax = sh_sum[6][threadIdx.x];
-    (void)dedt; (void)dhdt; (void)muijmax; (void)pi;
-#if SOLID
-    double vgrad[DIM][DIM];
-#pragma unroll
-    for (int a = 0; a < DIM; a++)
-#pragma unroll
-        for (int b = 0; b < DIM; b++) vgrad[a][b] = sh_sum[7 + a * DIM + b][threadIdx.x];
+    p.dalphadt[i] = dalphadt;
 #endif
-#include "forces_epilogue.inc"
+#if SOLID
+    if (noi < 1) {
+#pragma unroll
+        for (int a = 0; a < DD; a++) p.dSdt[(size_t)i * DD + a] = 0.0;
+#if FRAGMENTATION
+        p.dddt[i] = 0.0;
+#if PALPHA_POROSITY
+        p.ddamage_porjutzidt[i] = 0.0;
+#endif
+#endif
+        return;
+    }
+    {
+        const double shear = M.shear, bulk = M.bulk, young = M.young;
+        (void)bulk;
+        double edot[DIM][DIM], rdot[DIM][DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) {
+                edot[a][b] = vgrad[a][b] + vgrad[b][a];
+                rdot[a][b] = vgrad[a][b] - vgrad[b][a];
+            }
+        double S[DIM][DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) S[a][b] = p.S[(size_t)i * DD + a * DIM + b];
+        double tr = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) tr += edot[a][a];
+        const double pf = 1.0 - pr.plastic_f[i];
+        double K2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) {
+                /* Hooke + Jaumann rotation terms (src/internal_forces.cu:1028-1050) */
+                double ds = 2.0 * shear * edot[a][b];
+                double ep = pf * edot[a][b];
+                if (a == b) {
+                    ds -= 2.0 * shear * tr / 3.0;
+                    ep -= pf * tr / 3.0;
+                }
+#pragma unroll
+                for (int c = 0; c < DIM; c++) {
+                    ds = fma(S[a][c], rdot[b][c], ds);
+                    ds = fma(S[b][c], rdot[a][c], ds);
+                }
+#if PALPHA_POROSITY && STRESS_PALPHA_POROSITY
+                if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN || M.eos == EOS_TYPE_JUTZI_ANEOS)
+                    ds = p.f[i] / alpha_now * ds - 1.0 / (alpha_now * alpha_now) * S[a][b] * dalphadt;
+#endif
+                p.dSdt[(size_t)i * DD + a * DIM + b] = ds;
+                K2 = fma(ep, ep, K2);
+            }
+        p.edotp[i] = sqrt(2.0 / 3.0 * K2);
+#if ARTIFICIAL_VISCOSITY
+        p.muijmax[i] = muijmax;
+#endif
+        /* largest principal stress -> local scalar strain (Grady-Kipp) */
+        double sigma[DIM][DIM];
+        const double rho2 = s.gas4[k].z * s.gas4[k].z;
+#pragma unroll
+        for (int a = 0; a < DIM; a++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) sigma[a][b] = pr.sigma[(size_t)i * DD + a * DIM + b];
+        (void)rho2;
+        const double tensile_max = sym_max_eigenvalue(sigma);
+        double local_strain = tensile_max / young;
+#if FRAGMENTATION
+        {
+            const double di_tensile = pow(p.d[i], (double)DIM);
+            if (di_tensile < 1.0) {
+                local_strain = tensile_max / ((1.0 - di_tensile) * young);
+                const double c_g = 0.4 * sqrt((bulk + 4.0 * shear * (1.0 - di_tensile) / 3.0) / s.gas4[k].z);
+                int n_active = 0;
+                const int nf = p.numFlaws[i];
+                const double *fl = pr.flaws + (size_t)i * v.max_num_flaws;
+                for (int f = 0; f < nf; f++) n_active += (fl[f] < local_strain) ? 1 : 0;
+                p.numActiveFlaws[i] = max(n_active, p.numActiveFlaws[i]);
+                p.dddt[i] = n_active * c_g / pi.w;
+            } else {
+                local_strain = 0.0;
+                p.numActiveFlaws[i] = p.numFlaws[i];
+                p.dddt[i] = 0.0;
+                p.d[i] = 1.0;
+            }
+#if PALPHA_POROSITY
+            double ddp = 0.0;
+            if (M.eos == EOS_TYPE_JUTZI || M.eos == EOS_TYPE_JUTZI_MURNAGHAN || M.eos == EOS_TYPE_JUTZI_ANEOS) {
+                const double deld = 0.01, a0 = M.pj_alpha_0;
+                if (a0 > 1.0)
+                    ddp = -1.0 / DIM * pow(1.0 - (alpha_now - 1.0) / (a0 - 1.0) + deld, 1.0 / DIM - 1.0) /
+                          (pow(1.0 + deld, 1.0 / DIM) - pow(deld, 1.0 / DIM)) * 1.0 / (a0 - 1.0) * dalphadt;
+            }
+            p.ddamage_porjutzidt[i] = ddp;
+#endif
+        }
+#endif
+        p.local_strain[i] = local_strain;
+    }
+#endif /* SOLID */
 }
 
 /* ------------------------------------------------------------------ export of neighbour lists */
@@ -1896,8 +1985,7 @@ static int rhs_stage_search(b200sph_handle *h, const b200sph_view &v)
 #if INTEGRATE_DENSITY
         k_density<LIST_CHECK><<<blocks_for(n, T), T, h->pad_smem, st>>>(s, v, h->rho_sorted, n, h->d_flags);
 #else
-        if (h->pair_teams & 1) k_density_team<<<blocks_for(n, kTeamParticles), FORCES_TEAM_THREADS, h->pad_smem, st>>>(s, v, h->rho_sorted, n, h->d_flags);
-        else k_density<LIST_VALIDATE><<<blocks_for(n, T), T, h->pad_smem, st>>>(s, v, h->rho_sorted, n, h->d_flags);
+        k_density<LIST_VALIDATE><<<blocks_for(n, T), T, h->pad_smem, st>>>(s, v, h->rho_sorted, n, h->d_flags);
         h->lists_validated = 1;
 #endif
         launches++;
@@ -1925,10 +2013,7 @@ static int rhs_stage_pointwise(b200sph_handle *h, const b200sph_view &v)
     if (h->hook_after_pointwise) h->hook_after_pointwise(h, h->hook_ctx);
     CU(cudaEventRecord(h->ev[4], st));
 #if TENSORIAL_CORRECTION
-    if (h->pair_teams & 2) {
-        if (h->lists_validated) k_correction_team<LIST_EXACT><<<blocks_for(n, kTeamParticles), FORCES_TEAM_THREADS, 0, st>>>(s, v, n, h->d_flags);
-        else k_correction_team<LIST_VALIDATE><<<blocks_for(n, kTeamParticles), FORCES_TEAM_THREADS, 0, st>>>(s, v, n, h->d_flags);
-    } else if (h->lists_validated) k_correction<LIST_EXACT><<<blocks_for(n, T), T, 0, st>>>(s, v, n, h->d_flags);
+    if (h->lists_validated) k_correction<LIST_EXACT><<<blocks_for(n, T), T, 0, st>>>(s, v, n, h->d_flags);
     else k_correction<LIST_VALIDATE><<<blocks_for(n, T), T, 0, st>>>(s, v, n, h->d_flags);
     h->lists_validated = 1;
     h->stage_launches++;
@@ -1952,10 +2037,7 @@ static int rhs_stage_forces(b200sph_handle *h, const b200sph_view &v, int *offen
 #endif
     const int TF = h->forces_threads;
     const size_t forces_smem = (size_t)h->pad_smem + ((SOLID && B200_ITENSORS_SMEM) ? (size_t)TF * TEN_RECS * 4 * sizeof(double) : 0);
-    if (h->lists_validated && (h->pair_teams & 4)) {
-        const size_t team_smem = (size_t)h->pad_smem + ((SOLID && B200_ITENSORS_SMEM) ? (size_t)FORCES_TEAM_THREADS * TEN_RECS * 4 * sizeof(double) : 0);
-        k_forces_team<<<blocks_for(n, kTeamParticles), FORCES_TEAM_THREADS, team_smem, st>>>(s, v, n, h->d_flags);
-    } else if (h->lists_validated) k_forces<LIST_EXACT><<<blocks_for(n, TF), TF, forces_smem, st>>>(s, v, n, h->d_flags);
+    if (h->lists_validated) k_forces<LIST_EXACT><<<blocks_for(n, TF), TF, forces_smem, st>>>(s, v, n, h->d_flags);
     else k_forces<LIST_VALIDATE><<<blocks_for(n, TF), TF, forces_smem, st>>>(s, v, n, h->d_flags);
     k_list_stats<<<min(blocks_for(n, 256), h->n_sm * 4), 256, 0, st>>>(s, h->d_flags);
     launches += 2;

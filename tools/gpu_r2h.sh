@@ -21,6 +21,9 @@ done
 for w in impact nakamura; do
     for v in tsmem tsmem4 tcap4; do run $v $w B200SPH_LIBDIR=$PWD/miluphcuda_b200/lib_$v; done
 done
+for cs in 0.5 0.7; do run cell$cs impact B200SPH_CELL_SCALE=$cs; done
+run cell0.8 sedov B200SPH_CELL_SCALE=0.8
+run cell1.25 sedov B200SPH_CELL_SCALE=1.25
 run team4 giant_hydro B200SPH_PAIR_TEAMS=7
 run team4 giant_solid B200SPH_PAIR_TEAMS=7
 run lane giant_solid B200SPH_PAIR_TEAMS=0
