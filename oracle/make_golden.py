@@ -88,8 +88,12 @@ def ref_binary(config: str) -> str:
     return path
 
 
+class ReferenceTimeout(RuntimeError):
+    """The reference binary did not finish within the caller's limit (it is killed)."""
+
+
 def run_reference(sc: scenarios.Scenario, workdir: str, env_extra: dict, log_name: str = "ref.log", evolve: bool = False,
-                  decouple: bool = False, input_file: str | None = None, suffix: str = "") -> str:
+                  decouple: bool = False, input_file: str | None = None, suffix: str = "", timeout_s: float | None = None) -> str:
     """Run oracle/_ref/miluphcuda_<config><suffix> on the scenario (or on an existing input file in `workdir`) with
     `-I euler`, i.e. through oracle/ref_hook.cu; evolve=True lets the reference's own rk2_adaptive run first."""
     if input_file is None:
@@ -108,7 +112,10 @@ def run_reference(sc: scenarios.Scenario, workdir: str, env_extra: dict, log_nam
     env.update(env_extra)
     log = os.path.join(workdir, log_name)
     with open(log, "w") as fh:
-        rc = subprocess.call(cmd, cwd=workdir, stdout=fh, stderr=subprocess.STDOUT, env=env)
+        try:
+            rc = subprocess.call(cmd, cwd=workdir, stdout=fh, stderr=subprocess.STDOUT, env=env, timeout=timeout_s)
+        except subprocess.TimeoutExpired:
+            raise ReferenceTimeout(f"{os.path.basename(cmd[0])} did not finish within {timeout_s:.0f} s ({' '.join(time_args)})") from None
     if rc != 0:
         tail = open(log).read()[-3000:]
         raise RuntimeError(f"reference run failed rc={rc}\n{tail}")
@@ -133,9 +140,10 @@ def arrays_from_dump(config: str, d_in: dict, selfgravity: bool):
     return arrays, dict(n=n, max_num_flaws=max_flaws, selfgravity=selfgravity)
 
 
-def evolved_state(sc, workdir: str):
+def evolved_state(sc, workdir: str, timeout_s: float | None = None):
     """State of the scenario after the reference's own rk2_adaptive took >= EVOLVE_STEPS steps: (dump, accepted steps)."""
-    log = run_reference(sc, workdir, {"REF_DUMP": os.path.join(workdir, "evolved"), "REF_DUMP_STATE_ONLY": "1"}, evolve=True)
+    log = run_reference(sc, workdir, {"REF_DUMP": os.path.join(workdir, "evolved"), "REF_DUMP_STATE_ONLY": "1"}, evolve=True,
+                        timeout_s=timeout_s)
     text = open(log).read()
     acc = re.findall(r"Had to integrate (\d+) timesteps \((\d+) accepted, (\d+) rejected\)", text)
     d_in = read_dump(os.path.join(workdir, "evolved.in.bin"))
@@ -185,11 +193,12 @@ def make_golden(config: str, n, out_dir: str, stirred: bool = False) -> str:
     return path
 
 
-def time_reference(config: str, n: int, calls: int, warmup: int, keep_log: str | None = None, evolve: bool = False) -> dict:
+def time_reference(config: str, n: int, calls: int, warmup: int, keep_log: str | None = None, evolve: bool = False,
+                   timeout_s: float | None = None) -> dict:
     sc = scenarios.make(config, n)
     with tempfile.TemporaryDirectory() as wd:
         t0 = time.time()
-        log = run_reference(sc, wd, {"REF_TIMED": str(calls), "REF_WARMUP": str(warmup)}, evolve=evolve)
+        log = run_reference(sc, wd, {"REF_TIMED": str(calls), "REF_WARMUP": str(warmup)}, evolve=evolve, timeout_s=timeout_s)
         text = open(log).read()
         wall = time.time() - t0
         if keep_log:
