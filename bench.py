@@ -604,11 +604,21 @@ def main() -> None:
             with open(tpath) as fh:
                 traffic = (json.load(fh).get(workload) or {}).get("k_forces_dram_bytes_per_launch")
             traffic_source = "profiles/" + tname if traffic is not None else None
+    # busiest unit of the kernel in the committed full capture (the gather's L1TEX data pipe), reported beside the FP64 fraction
+    l1_pipe = None
+    lpath = os.path.join(REPO, "profiles", "r02_ncu_l1_pipe.json")
+    if os.path.exists(lpath):
+        with open(lpath) as fh:
+            lp = json.load(fh)
+        if workload in lp:
+            l1_pipe = {"frac_of_peak_wavefront_rate": lp[workload].get("k_forces"), "fp64_pipe_busy": lp[workload].get("k_forces_fp64_pipe"),
+                       "issue_active": lp[workload].get("k_forces_issue_active"), "source": "profiles/r02_ncu_l1_pipe.json (ncu --set full capture, not this run)"}
     roof = {"bound": "fp64", "kernel": "k_forces", "achieved": tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
             "frac": tf / peaks["fp64_tflops"], "traffic": traffic, "traffic_source": traffic_source, "peak_source": peaks["fp64_source"],
             "ms_per_launch": ms_forces, "pairs_per_launch": pairs, "flop_per_pair": kind["force_flop_per_pair"],
             "hbm": {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                     "peak_source": peaks["hbm_source"], "bytes_per_particle": kind["force_bytes_per_particle"]},
+            "l1tex_data_pipe": l1_pipe,
             "share_of_step": ms_forces * args.steps / total_ms if total_ms > 0 else None,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}}
 
