@@ -1259,17 +1259,6 @@ __global__ void k_import_correction(Sorted s, b200sph_view v)
 }
 #endif
 
-#ifndef B200_ITENSORS_SMEM
-#define B200_ITENSORS_SMEM 0   /* A/B switch of tools/gpu_r2g.sh, see the comment at its use in k_forces */
-#endif
-__device__ __forceinline__ double lds_f64(const double *ptr)
-{
-    /* volatile: the compiler must not hoist the loop-invariant load back into a register */
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned int)__cvta_generic_to_shared(ptr)));
-    return v;
-}
-
 /* ------------------------------------------------------------------ k_forces */
 __device__ __forceinline__ double int_power(double x, int n)
 {
@@ -1292,10 +1281,7 @@ __device__ __forceinline__ double int_power(double x, int n)
 #endif
 #endif
 #if B200_FORCES_MIN_BLOCKS > 1
-#ifndef B200_FORCES_BOUND_THREADS
-#define B200_FORCES_BOUND_THREADS 128
-#endif
-#define FORCES_BOUNDS __launch_bounds__(B200_FORCES_BOUND_THREADS, B200_FORCES_MIN_BLOCKS)
+#define FORCES_BOUNDS __launch_bounds__(128, B200_FORCES_MIN_BLOCKS)
 #else
 #define FORCES_BOUNDS __launch_bounds__(128)   /* not (128, 1): that form makes ptxas take 190 registers for the 3-D solid loop */
 #endif
@@ -1327,21 +1313,12 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
     for (int a = 0; a < DIM; a++)
 #pragma unroll
         for (int b = 0; b < DIM; b++) vgrad[a][b] = 0.0;
-#if B200_ITENSORS_SMEM
-    /* the particle's own tensors (sigma/rho^2, C, R/rho^2: up to 18 doubles) live in shared memory, one column per
-     * thread (conflict-free), and are re-read per pair instead of pinning 24-36 registers for the whole loop */
-    extern __shared__ double sh_ti[];
-    double *const my_ti = sh_ti + threadIdx.x;
-    const int ti_stride = blockDim.x;
-#define TI(idx) lds_f64(my_ti + (idx) * ti_stride)
-#else
     double sig_i[DIM][DIM];
 #if TENSORIAL_CORRECTION
     double Ci[DIM][DIM];
 #endif
 #if ARTIFICIAL_STRESS
     double Ri[DIM][DIM];
-#endif
 #endif
 #endif
 
@@ -1364,10 +1341,6 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
                 const Rec4 t = ld_rec(&s.ten[(size_t)k * TEN_RECS + r]);
                 ti[4 * r] = t.x; ti[4 * r + 1] = t.y; ti[4 * r + 2] = t.z; ti[4 * r + 3] = t.w;
             }
-#if B200_ITENSORS_SMEM
-#pragma unroll
-            for (int c = 0; c < TEN_DOUBLES; c++) my_ti[c * ti_stride] = ti[c];
-#else
 #pragma unroll
             for (int a = 0; a < DIM; a++)
 #pragma unroll
@@ -1380,7 +1353,6 @@ k_forces(Sorted s, b200sph_view v, int n_targets, int *flags)
                     Ri[a][b] = ti[ten_r(a, b)];
 #endif
                 }
-#endif
         }
         const double m_over_rho_i_unit = 1.0 / rho_i;   /* strain rate uses m_j / rho_i (src/internal_forces.cu:476) */
 #endif
@@ -1440,32 +1412,6 @@ PAIR_UNROLL
             for (int a = 0; a < DIM; a++) gw[a] = g * dr[a];
             const double mj = vj.w;
 
-#if SOLID && B200_ITENSORS_SMEM
-            double sig_i[DIM][DIM];
-#if TENSORIAL_CORRECTION
-            double Ci[DIM][DIM];
-#endif
-#if ARTIFICIAL_STRESS
-            double Ri[DIM][DIM];
-#endif
-#pragma unroll
-            for (int a = 0; a < DIM; a++)
-#pragma unroll
-                for (int b = a; b < DIM; b++) {
-#if TEN_SIG_SYM
-                    sig_i[a][b] = sig_i[b][a] = TI(ten_sig(a, b));
-#else
-                    sig_i[a][b] = TI(ten_sig(a, b));
-                    if (a != b) sig_i[b][a] = TI(ten_sig(b, a));
-#endif
-#if TENSORIAL_CORRECTION
-                    Ci[a][b] = Ci[b][a] = TI(ten_c(a, b));
-#endif
-#if ARTIFICIAL_STRESS
-                    Ri[a][b] = Ri[b][a] = TI(ten_r(a, b));
-#endif
-                }
-#endif
 #if TENSORIAL_CORRECTION
             double gci[DIM], gcj[DIM], gsym[DIM];
 #pragma unroll
@@ -2036,7 +1982,7 @@ static int rhs_stage_forces(b200sph_handle *h, const b200sph_view &v, int *offen
     }
 #endif
     const int TF = h->forces_threads;
-    const size_t forces_smem = (size_t)h->pad_smem + ((SOLID && B200_ITENSORS_SMEM) ? (size_t)TF * TEN_RECS * 4 * sizeof(double) : 0);
+    const size_t forces_smem = (size_t)h->pad_smem;
     if (h->lists_validated) k_forces<LIST_EXACT><<<blocks_for(n, TF), TF, forces_smem, st>>>(s, v, n, h->d_flags);
     else k_forces<LIST_VALIDATE><<<blocks_for(n, TF), TF, forces_smem, st>>>(s, v, n, h->d_flags);
     k_list_stats<<<min(blocks_for(n, 256), h->n_sm * 4), 256, 0, st>>>(s, h->d_flags);
