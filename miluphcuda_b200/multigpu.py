@@ -162,9 +162,18 @@ def morton_partition(x: np.ndarray, world: int, level: int | None = None):
     return dec, [np.nonzero(owner == r)[0] for r in range(world)]
 
 
-def halo_levels(switches: dict) -> int:
-    """2 when neighbours' own neighbour sums are needed (kernel-sum density or tensorial correction), else 1."""
-    if not switches.get("INTEGRATE_DENSITY", 0) or switches.get("TENSORIAL_CORRECTION", 0):
+def halo_levels(switches: dict, kernel_sum_materials: bool = False) -> int:
+    """2 when neighbours' own neighbour sums are needed (kernel-sum density or tensorial correction), else 1.
+
+    Kernel-sum density TOGETHER with the tensorial correction (an INTEGRATE_DENSITY build whose material.cfg asks for
+    density_via_kernel_sum, or a build without INTEGRATE_DENSITY) would need a third level in the state-only halo: the
+    correction matrix of a first-level copy sums m/rho over second-level copies whose kernel-sum rho is incomplete.
+    That combination is only served by the neighbour-sum exchange (DistributedRhs(external_sums=True) on GPUs, one level);
+    the state-only halo refuses it instead of returning wrong matrices."""
+    kernel_sum = (not switches.get("INTEGRATE_DENSITY", 0)) or kernel_sum_materials
+    if kernel_sum and switches.get("TENSORIAL_CORRECTION", 0):
+        return 3
+    if kernel_sum or switches.get("TENSORIAL_CORRECTION", 0):
         return 2
     return 1
 
@@ -233,6 +242,9 @@ class HaloExchange:
         f = self.fields
         dev = f["x"].device
         eng = self.engine
+        # the library's pack / unpack / plan kernels and torch's collectives must share one stream:
+        # do it here, not only in the callers
+        eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
         eng.halo_set_domains(self.boxes, self.box_rank, self.world, self.rank)
         self._desc = eng.halo_fields(f, self.exchange, self.capacity)
         self._sum_desc = {}
@@ -506,8 +518,12 @@ class DistributedRhs:
         # GPU buffers: ONE halo level; density / correction matrix of the copies are delivered by their owners between
         # the stages of the evaluation (neighbour-sum exchange).  CPU tensors (gloo tests, oracle as the evaluator): the
         # two-level halo, where the evaluator completes those sums itself.
-        self.external_sums = bool(on_gpu and world > 1 and external_sums and halo_levels(switches) == 2)
-        levels = 1 if self.external_sums else halo_levels(switches)
+        need = halo_levels(switches, bool(meta.get("kernel_sum_materials")))
+        self.external_sums = bool(on_gpu and world > 1 and external_sums and need >= 2)
+        levels = 1 if self.external_sums else need
+        if levels > 2:
+            raise NotImplementedError("kernel-sum density together with the tensorial correction needs the neighbour-sum exchange "
+                                      "(GPU buffers, external_sums=True); the state-only halo has two levels")
         self.halo = HaloExchange(fields, capacity, dec, levels=levels, group=group, engine=engine, h_evolves=h_evolves)
         self.halo.device_verdict = bool(on_gpu and world > 1 and device_verdict)
         self.sum_exchanges = 0
