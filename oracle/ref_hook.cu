@@ -37,6 +37,7 @@
 
 #include <stdint.h>
 #include <stdio.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -186,6 +187,9 @@ void euler()
          * format is chosen, src/io.cu:1567-1570; HDF5 is compiled out in this build), only the small .info / log files */
         param.ascii_output = FALSE;
         param.hdf5output = TRUE;
+        struct timespec ts0, ts1;   /* wall clock of the integrator call itself (tools/integrator_speed.py) */
+        cudaVerify(cudaDeviceSynchronize());
+        clock_gettime(CLOCK_MONOTONIC, &ts0);
         if (0 == strcmp(s_evolve, "pc")) {
             param.integrator_type = MONAGHAN_PC;
             predictor_corrector();
@@ -194,6 +198,8 @@ void euler()
             rk2Adaptive();
         }
         cudaVerify(cudaDeviceSynchronize());
+        clock_gettime(CLOCK_MONOTONIC, &ts1);
+        fprintf(stdout, "REF_EVOLVE_WALL_MS=%.3f\n", (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
         if (currentDiskIO) pthread_join(fileIOthread, NULL);   /* the writer thread of the last output step */
         cudaVerify(cudaMemcpyToSymbol(p, &p_device, sizeof(struct Particle)));
         fprintf(stdout, "REF_EVOLVED t=%.17e\n", currentTime);
