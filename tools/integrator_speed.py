@@ -34,6 +34,19 @@ def measure(config: str, n: int) -> dict:
         text = open(log).read()
         acc = re.findall(r"Had to integrate (\d+) timesteps \((\d+) accepted, (\d+) rejected\)", text)[-1]
         ref_ms = float(re.search(r"REF_EVOLVE_WALL_MS=([\d.]+)", text).group(1))
+        # the drop-in binary: the reference's host and integrator (its ~120 device-to-device copies per step included) on
+        # this library's right-hand side (integration/rhs_b200.cu)
+        dropin_ms, dropin_acc, dropin_err = None, None, None
+        if os.path.exists(make_golden.ref_binary(config) + "_b200"):
+            with tempfile.TemporaryDirectory() as wd2:
+                log2 = make_golden.run_reference(sc, wd2, {"REF_DUMP": os.path.join(wd2, "s"), "REF_DUMP_STATE_ONLY": "1"}, evolve=True,
+                                                 suffix="_b200", timeout_s=900)
+                text2 = open(log2).read()
+                dropin_ms = float(re.search(r"REF_EVOLVE_WALL_MS=([\d.]+)", text2).group(1))
+                a2 = re.findall(r"Had to integrate (\d+) timesteps \((\d+) accepted, (\d+) rejected\)", text2)[-1]
+                dropin_acc = {"accepted": int(a2[1]), "rejected": int(a2[2])}
+                d2 = make_golden.read_dump(os.path.join(wd2, "s.in.bin"))
+                dropin_err = max(float(common.field_error(d2[k], ref[k])) for k in INTEGRATED if k in d2 and k in ref and d2[k].shape == ref[k].shape)
         args = make_golden.evolve_args(sc)
         t_end, dt_max, eps = float(args[args.index("-t") + 1]), float(args[args.index("-M") + 1]), float(args[args.index("-Q") + 1])
         arrays, meta = make_golden.arrays_from_dump(config, start, bool(sc.selfgravity))
@@ -63,6 +76,8 @@ def measure(config: str, n: int) -> dict:
            "steps_b200": {"accepted": st.accepted, "rejected": st.rejected, "rhs_calls": st.rhs_calls},
            "reference_rk2Adaptive_wall_ms": ref_ms, "reference_process_wall_s": ref_process_s,
            "b200_rk2_advance_wall_ms": ours_ms, "ratio": ref_ms / ours_ms,
+           "dropin_binary_rk2Adaptive_wall_ms": dropin_ms, "dropin_ratio": (ref_ms / dropin_ms) if dropin_ms else None,
+           "dropin_steps": dropin_acc, "dropin_max_field_error": dropin_err,
            "ms_per_accepted_step": {"reference": ref_ms / max(int(acc[1]), 1), "b200": ours_ms / max(st.accepted, 1)},
            "max_field_error_after_run": max(worst.values()) if worst else None, "field_errors": worst,
            "what": ("reference: rk2Adaptive() of the unmodified CUDA build (device-resident, no particle output), host clock around the call; "
