@@ -96,3 +96,66 @@ def test_fp32_prefilter_never_rejects_an_exact_neighbour():
         checked += int(exact.sum())
         assert far.sum() > 1000 and not (hit & far).any(), "pairs clearly outside the support survive the FP32 filter"
     assert checked > 100000
+
+
+def test_row_clipping_keeps_every_exact_neighbour():
+    """k_neighbours scans rows of x-adjacent cells clipped to the sphere (csrc/rhs_kernels.cu: stencil_of, row_gap, the
+    FP32 square root rounded up).  Restated in numpy: for random targets and random exact neighbours (d < h_i^2), the
+    neighbour's cell lies inside the stencil, its row is not skipped, and its cell index lies inside the clipped x range --
+    including particles on cell faces, in the clamped outermost cells and beyond the grid."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+
+    def cell_coord(x, lo, cell_inv, nc):
+        c = ((x - lo) * cell_inv).astype(np.int64)        # truncation like the (int) cast (arguments are >= lo - reach)
+        c = np.where((x - lo) * cell_inv < 0, np.ceil((x - lo) * cell_inv).astype(np.int64), c)
+        return np.clip(c, 0, nc - 1)
+
+    def row_gap(p, lo, cell, c, nc, slack):
+        c_lo = c * cell + lo
+        below = np.where(c > 0, c_lo - p, -1.0)
+        above = np.where(c < nc - 1, p - (c_lo + cell), -1.0)
+        return np.maximum(np.maximum(below, above) - slack, 0.0)
+
+    total = 0
+    for cell, nc, lo0 in ((0.5, 40, -3.0), (1.0e-2, 700, 100.0), (2.5e4, 64, -8.0e5)):
+        n = 300000
+        lo = np.array([lo0, lo0 + 0.3 * cell, lo0 - 0.7 * cell])
+        ncs = np.array([nc, max(nc // 2, 3), max(nc // 3, 3)])
+        cell_inv = 1.0 / cell
+        # targets: inside the grid, a tenth exactly on cell faces, a tenth outside the grid (clamped outermost cells)
+        p = lo + rng.random((n, 3)) * ncs * cell
+        on_face = rng.random(n) < 0.1
+        p[on_face] = lo + np.floor((p[on_face] - lo) * cell_inv) * cell
+        outside = rng.random(n) < 0.1
+        p[outside] += (rng.random((int(outside.sum()), 3)) - 0.5) * 6.0 * cell
+        h = cell * (0.3 + rng.random(n) * 3.5)             # from a third of a cell to 3.8 cells
+        direction = rng.normal(size=(n, 3))
+        direction /= np.linalg.norm(direction, axis=1)[:, None]
+        q = p + direction * (h * (1.0 - 10.0 ** rng.uniform(-12, 0, n)))[:, None]   # neighbours from r ~ 0 up to the edge
+        d = p - q
+        r2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+        exact = r2 < h * h
+        reach = (h * cell_inv + 1e-9).astype(np.int64) + 1
+        cp = [cell_coord(p[:, a], lo[a], cell_inv, ncs[a]) for a in range(3)]
+        cq = [cell_coord(q[:, a], lo[a], cell_inv, ncs[a]) for a in range(3)]
+        for a in range(3):
+            inside = (cq[a] >= np.maximum(cp[a] - reach, 0)) & (cq[a] <= np.minimum(cp[a] + reach, ncs[a] - 1))
+            assert inside[exact].all(), f"axis {a}: an exact neighbour lies outside the stencil"
+        reach2 = (h * h) * (1.0 + 1e-9)
+        slack = 1e-9 * cell
+        gz = row_gap(p[:, 2], lo[2], cell, cq[2], ncs[2], slack)
+        rem_z = reach2 - gz * gz
+        gy = row_gap(p[:, 1], lo[1], cell, cq[1], ncs[1], slack)
+        rem = rem_z - gy * gy
+        assert (rem_z[exact] > 0.0).all() and (rem[exact] > 0.0).all(), "the row of an exact neighbour is skipped"
+        rem_f = _f32_up(np.maximum(rem, 0.0))
+        root = np.sqrt(rem_f.astype(np.float64))
+        root_f = _f32_up(root)                              # __fsqrt_ru
+        w = root_f.astype(np.float64) * (1.0 + 1e-6) + slack
+        xa = np.maximum(np.maximum(cp[0] - reach, 0), cell_coord(p[:, 0] - w, lo[0], cell_inv, ncs[0]))
+        xb = np.minimum(np.minimum(cp[0] + reach, ncs[0] - 1), cell_coord(p[:, 0] + w, lo[0], cell_inv, ncs[0]))
+        ok = (cq[0] >= xa) & (cq[0] <= xb)
+        assert ok[exact].all(), f"{int((~ok & exact).sum())} exact neighbours fall outside the clipped x range of their row"
+        total += int(exact.sum())
+    assert total > 500000
