@@ -144,7 +144,8 @@ def run_reference_arm(args, rank: int, world: int) -> None:
             "config": {"workload": f"{workload} (synthetic, {n} particles requested)", "particles": n}}
     if os.path.exists(binary):
         import make_golden
-        evolve = (args.state or "evolved") == "evolved"
+        # the same state rule as the library arm: evolved on one GPU, step 0 when the library arm is distributed
+        evolve = (args.state or ("evolved" if world == 1 else "step0")) == "evolved"
         try:
             res = make_golden.time_reference(workload, n, calls=args.steps, warmup=args.warmup, evolve=evolve,
                                              timeout_s=EVOLVE_TIMEOUT_S if evolve else None)
